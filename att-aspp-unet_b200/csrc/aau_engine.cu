@@ -1,0 +1,963 @@
+// libaau: host engine + C ABI (include/aau.h) around the sm_100a kernels in igemm_tc.cuh / hbm_kernels.cuh.
+//
+// What lives here (all host C++):
+//   * the state_dict contract of the reference model (key names / shapes),
+//   * weight preparation: BatchNorm folding in fp32 (eps 1e-5), one rounding to the 16-bit activation type,
+//     K-major re-layout for the tensor cores, upload,
+//   * the per-(B,H,W) launch plan: NHWC workspace carving, TMA tensor maps, tile-shape / pipeline-depth choice,
+//   * aau_forward / aau_frame_scores, which only enqueue kernels on the caller's stream.
+// Reference graph being reproduced: attention_aspp_unet_pipeline_stage.py:111-127 (and test_ablation.py:168-218).
+#include "../../include/aau.h"
+#include "hbm_kernels.cuh"
+
+#include <cudaTypedefs.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace aau {
+
+static thread_local std::string g_create_error;
+
+#define AAU_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            return e.fail(AAU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+        }                                                                                                \
+    } while (0)
+
+enum KeyKind { KK_W = 0, KK_BIAS, KK_BN_W, KK_BN_B, KK_BN_M, KK_BN_V };
+struct KeySpec {
+    std::string name;
+    int64_t numel;
+    int kind;
+};
+
+struct GemmW {                // packed GEMM operand, device resident
+    void* dB = nullptr;       // [N][K] 16-bit, K contiguous
+    float* dbias = nullptr;   // fp32
+    float* dvec = nullptr;    // optional fp32 vector (gate w_psi, out_conv w)
+    float scalar = 0.f;       // optional scalar (gate b_psi, out_conv b)
+    int N = 0, K = 0, Cin = 0, taps = 1;
+};
+
+struct View {                 // NHWC 16-bit tensor view inside a (possibly concatenated) buffer
+    uint8_t* p = nullptr;
+    int B = 0, H = 0, W = 0, C = 0, ld = 0, choff = 0;
+    size_t bytes() const { return (size_t)B * H * W * ld * 2; }
+};
+
+struct ConvDesc {             // one GEMM problem
+    const GemmW* w = nullptr;
+    View in;                  // Cin = in.C
+    int dil = 1;
+    int epi = EPI_STORE, relu = 1;
+    const float* bias_img = nullptr;
+    int bias_img_stride = 0;
+    View out;                 // STORE/CONVT destination, GATE: skip view (C = gate_C)
+    int convt_cout = 0;
+    float* aux = nullptr;
+    int gate_plus_x = 0;
+};
+
+struct FwdArgs {
+    const void* x;
+    int x_dtype;
+    float* logits;
+    float* psi3;
+    float* psi2;
+    cudaStream_t stream;
+};
+
+struct Plan {
+    int B = 0, H = 0, W = 0;
+    void* ws = nullptr;
+    std::vector<std::function<cudaError_t(const FwdArgs&)>> ops;
+    std::map<std::string, View> named;
+};
+
+struct Engine {
+    aau_config cfg{};
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    std::vector<KeySpec> keys;
+    std::map<std::string, std::vector<float>> host;   // loaded state_dict entries
+    int unexpected = 0;
+    bool committed = false;
+    std::map<std::string, GemmW> gw;                  // by layer name
+    float *d_stem_w = nullptr, *d_stem_b = nullptr;   // [9][c], [c]
+    float *d_poolT = nullptr, *d_poolb = nullptr, *d_projT = nullptr, *d_projb = nullptr;
+    std::vector<void*> dev_allocs;
+    std::vector<std::unique_ptr<Plan>> plans;
+    int* d_err = nullptr;
+    int last_launches = 0;
+    int opt_amode = -1;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    bool is_fp16() const { return cfg.act_dtype == AAU_ACT_FP16; }
+    bool pipeline() const { return cfg.variant == AAU_VARIANT_PIPELINE; }
+    bool has_aspp() const { return pipeline() || cfg.use_aspp; }
+    bool has_gate(int lvl) const {
+        if (pipeline()) return lvl >= 2;
+        if (!cfg.use_att) return false;
+        return (lvl == 4 && cfg.att_depth >= 4) || (lvl == 3 && cfg.att_depth >= 3);
+    }
+    int f_int(int lvl) const {
+        const int out_c = cfg.base_c << (lvl - 1);
+        return pipeline() ? out_c / 2 : std::max(8, out_c / 4);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// state_dict layout
+// ------------------------------------------------------------------------------------------------------------
+static void add_bn(std::vector<KeySpec>& k, const std::string& p, int n) {
+    k.push_back({p + ".weight", n, KK_BN_W});
+    k.push_back({p + ".bias", n, KK_BN_B});
+    k.push_back({p + ".running_mean", n, KK_BN_M});
+    k.push_back({p + ".running_var", n, KK_BN_V});
+}
+static void add_cbr(std::vector<KeySpec>& k, const std::string& p, int cin, int cout) {
+    k.push_back({p + ".block.0.weight", (int64_t)cout * cin * 9, KK_W});
+    add_bn(k, p + ".block.1", cout);
+}
+static void build_keys(Engine& e) {
+    auto& k = e.keys;
+    const int c = e.cfg.base_c;
+    const int ch[5] = {e.cfg.in_channels, c, 2 * c, 4 * c, 8 * c};
+    for (int l = 1; l <= 4; ++l) {
+        add_cbr(k, "d" + std::to_string(l) + ".0", ch[l - 1], ch[l]);
+        add_cbr(k, "d" + std::to_string(l) + ".1", ch[l], ch[l]);
+    }
+    const int ic = 8 * c, oc = 16 * c;
+    if (e.has_aspp()) {
+        k.push_back({"bridge.blocks.0.0.weight", (int64_t)oc * ic, KK_W});
+        add_bn(k, "bridge.blocks.0.1", oc);
+        for (int i = 1; i <= 3; ++i) {
+            k.push_back({"bridge.blocks." + std::to_string(i) + ".0.weight", (int64_t)oc * ic * 9, KK_W});
+            add_bn(k, "bridge.blocks." + std::to_string(i) + ".1", oc);
+        }
+        k.push_back({"bridge.pool.1.weight", (int64_t)oc * ic, KK_W});
+        add_bn(k, "bridge.pool.2", oc);
+        k.push_back({"bridge.project.0.weight", (int64_t)oc * 5 * oc, KK_W});
+        add_bn(k, "bridge.project.1", oc);
+    } else {
+        add_cbr(k, "bridge.0", ic, oc);
+    }
+    for (int l = 4; l >= 1; --l) {
+        const int out_c = c << (l - 1), in_c = 2 * out_c;
+        const std::string p = "u" + std::to_string(l);
+        k.push_back({p + ".up.weight", (int64_t)in_c * out_c * 4, KK_W});
+        k.push_back({p + ".up.bias", out_c, KK_BIAS});
+        if (e.has_gate(l)) {
+            const int fi = e.f_int(l);
+            if (e.pipeline()) {
+                k.push_back({p + ".att.Wg.0.weight", (int64_t)fi * out_c, KK_W});
+                add_bn(k, p + ".att.Wg.1", fi);
+                k.push_back({p + ".att.Wx.0.weight", (int64_t)fi * out_c, KK_W});
+                add_bn(k, p + ".att.Wx.1", fi);
+                k.push_back({p + ".att.psi.0.weight", fi, KK_W});
+                add_bn(k, p + ".att.psi.1", 1);
+            } else {
+                k.push_back({p + ".att.Wg.weight", (int64_t)fi * out_c, KK_W});
+                k.push_back({p + ".att.Wx.weight", (int64_t)fi * out_c, KK_W});
+                k.push_back({p + ".att.psi.1.weight", fi, KK_W});
+                k.push_back({p + ".att.psi.1.bias", 1, KK_BIAS});
+            }
+        }
+        add_cbr(k, p + ".conv.0", in_c, out_c);
+        add_cbr(k, p + ".conv.1", out_c, out_c);
+    }
+    k.push_back({"out_conv.weight", c, KK_W});
+    k.push_back({"out_conv.bias", 1, KK_BIAS});
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight preparation
+// ------------------------------------------------------------------------------------------------------------
+struct Prep {
+    Engine& e;
+    std::string missing;
+    explicit Prep(Engine& en) : e(en) {}
+    const std::vector<float>* get(const std::string& key) {
+        auto it = e.host.find(key);
+        if (it == e.host.end()) {
+            if (missing.empty()) missing = key;
+            return nullptr;
+        }
+        return &it->second;
+    }
+    // scale / shift of an eval-mode BatchNorm2d; module defaults (gamma 1, beta 0, mean 0, var 1) when absent
+    void bn(const std::string& p, int n, std::vector<double>& s, std::vector<double>& t) {
+        auto g = e.host.find(p + ".weight"), b = e.host.find(p + ".bias");
+        auto m = e.host.find(p + ".running_mean"), v = e.host.find(p + ".running_var");
+        s.resize(n);
+        t.resize(n);
+        for (int i = 0; i < n; ++i) {
+            const double gamma = g != e.host.end() ? g->second[i] : 1.0, beta = b != e.host.end() ? b->second[i] : 0.0;
+            const double mu = m != e.host.end() ? m->second[i] : 0.0, var = v != e.host.end() ? v->second[i] : 1.0;
+            s[i] = gamma / std::sqrt(var + 1e-5);
+            t[i] = beta - mu * s[i];
+        }
+    }
+};
+
+static uint16_t to16(float f, bool fp16) {
+    if (fp16) {
+        __half h = __float2half_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+
+template <typename T>
+static cudaError_t upload(Engine& e, const std::vector<T>& v, T** out) {
+    void* p = nullptr;
+    cudaError_t r = cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 256));
+    if (r != cudaSuccess) return r;
+    e.dev_allocs.push_back(p);
+    r = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (T*)p;
+    return r;
+}
+
+static int finish_gemm(Engine& e, GemmW& g, const std::vector<float>& Bm, const std::vector<float>& bias) {
+    std::vector<uint16_t> b16(Bm.size());
+    const bool f16 = e.is_fp16();
+    for (size_t i = 0; i < Bm.size(); ++i) b16[i] = to16(Bm[i], f16);
+    uint16_t* d = nullptr;
+    if (upload(e, b16, &d) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "weight upload failed");
+    g.dB = d;
+    if (upload(e, bias, &g.dbias) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "bias upload failed");
+    return AAU_OK;
+}
+
+// ConvBNReLU (3x3) or a BN-folded 1x1: B[o][tap*Cin + i] = W[o][i][ky][kx] * s[o]
+static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::string& wkey, const std::string& bnp,
+                        int cin, int cout, int taps) {
+    const std::vector<float>* w = P.get(wkey);
+    if (!w) return AAU_OK;   // reported once by the caller through P.missing
+    std::vector<double> s, t;
+    P.bn(bnp, cout, s, t);
+    GemmW g;
+    g.N = cout; g.Cin = cin; g.taps = taps; g.K = taps * cin;
+    std::vector<float> Bm((size_t)g.N * g.K), bias(cout);
+    for (int o = 0; o < cout; ++o) {
+        bias[o] = (float)t[o];
+        for (int i = 0; i < cin; ++i)
+            for (int tp = 0; tp < taps; ++tp)
+                Bm[(size_t)o * g.K + (size_t)tp * cin + i] = (float)((double)(*w)[((size_t)o * cin + i) * taps + tp] * s[o]);
+    }
+    int r = finish_gemm(e, g, Bm, bias);
+    e.gw[name] = g;
+    return r;
+}
+
+static int commit_weights(Engine& e) {
+    for (void* p : e.dev_allocs) cudaFree(p);
+    e.dev_allocs.clear();
+    e.gw.clear();
+    e.plans.clear();
+    e.committed = false;
+    Prep P(e);
+    const int c = e.cfg.base_c;
+    const int ch[5] = {1, c, 2 * c, 4 * c, 8 * c};
+    int r;
+    // ---- d1.0 (direct conv, fp32 weights): w[tap][o] = W[o][0][ky][kx] * s[o]
+    {
+        const std::vector<float>* w = P.get("d1.0.block.0.weight");
+        std::vector<double> s, t;
+        P.bn("d1.0.block.1", c, s, t);
+        if (w) {
+            std::vector<float> w9c((size_t)9 * c), b(c);
+            for (int o = 0; o < c; ++o) {
+                b[o] = (float)t[o];
+                for (int tp = 0; tp < 9; ++tp) w9c[(size_t)tp * c + o] = (float)((double)(*w)[(size_t)o * 9 + tp] * s[o]);
+            }
+            if (upload(e, w9c, &e.d_stem_w) != cudaSuccess || upload(e, b, &e.d_stem_b) != cudaSuccess)
+                return e.fail(AAU_ERR_CUDA, "stem upload failed");
+        }
+    }
+    if ((r = prep_conv_bn(e, P, "d1.1", "d1.1.block.0.weight", "d1.1.block.1", c, c, 9))) return r;
+    for (int l = 2; l <= 4; ++l) {
+        const std::string p = "d" + std::to_string(l);
+        if ((r = prep_conv_bn(e, P, p + ".0", p + ".0.block.0.weight", p + ".0.block.1", ch[l - 1], ch[l], 9))) return r;
+        if ((r = prep_conv_bn(e, P, p + ".1", p + ".1.block.0.weight", p + ".1.block.1", ch[l], ch[l], 9))) return r;
+    }
+    const int ic = 8 * c, oc = 16 * c;
+    if (e.has_aspp()) {
+        if ((r = prep_conv_bn(e, P, "aspp.0", "bridge.blocks.0.0.weight", "bridge.blocks.0.1", ic, oc, 1))) return r;
+        for (int i = 1; i <= 3; ++i)
+            if ((r = prep_conv_bn(e, P, "aspp." + std::to_string(i), "bridge.blocks." + std::to_string(i) + ".0.weight",
+                                  "bridge.blocks." + std::to_string(i) + ".1", ic, oc, 9)))
+                return r;
+        // image-pooling branch: transposed fp32 weights for the per-image bias kernel
+        const std::vector<float>* wp = P.get("bridge.pool.1.weight");
+        const std::vector<float>* wj = P.get("bridge.project.0.weight");
+        std::vector<double> sp, tp, sj, tj;
+        P.bn("bridge.pool.2", oc, sp, tp);
+        P.bn("bridge.project.1", oc, sj, tj);
+        if (wp && wj) {
+            std::vector<float> poolT((size_t)ic * oc), poolb(oc), projT((size_t)oc * oc), projb(oc);
+            for (int o = 0; o < oc; ++o) {
+                poolb[o] = (float)tp[o];
+                projb[o] = (float)tj[o];
+                for (int i = 0; i < ic; ++i) poolT[(size_t)i * oc + o] = (float)((double)(*wp)[(size_t)o * ic + i] * sp[o]);
+                for (int j = 0; j < oc; ++j) projT[(size_t)j * oc + o] = (float)((double)(*wj)[(size_t)o * 5 * oc + 4 * oc + j] * sj[o]);
+            }
+            if (upload(e, poolT, &e.d_poolT) != cudaSuccess || upload(e, poolb, &e.d_poolb) != cudaSuccess ||
+                upload(e, projT, &e.d_projT) != cudaSuccess || upload(e, projb, &e.d_projb) != cudaSuccess)
+                return e.fail(AAU_ERR_CUDA, "aspp pool upload failed");
+            // project over the four conv branches only (K = 4*oc); its bias arrives per image
+            GemmW g;
+            g.N = oc; g.Cin = 4 * oc; g.taps = 1; g.K = 4 * oc;
+            std::vector<float> Bm((size_t)g.N * g.K), bias(oc, 0.f);
+            for (int o = 0; o < oc; ++o)
+                for (int k = 0; k < g.K; ++k) Bm[(size_t)o * g.K + k] = (float)((double)(*wj)[(size_t)o * 5 * oc + k] * sj[o]);
+            if ((r = finish_gemm(e, g, Bm, bias))) return r;
+            e.gw["aspp.project"] = g;
+        }
+    } else {
+        if ((r = prep_conv_bn(e, P, "bridge.0", "bridge.0.block.0.weight", "bridge.0.block.1", ic, oc, 9))) return r;
+    }
+    for (int l = 4; l >= 1; --l) {
+        const int out_c = c << (l - 1), in_c = 2 * out_c;
+        const std::string p = "u" + std::to_string(l);
+        // ConvTranspose2d(in_c, out_c, 2, 2): B[(a*2+b)*out_c + co][i] = W[i][co][a][b]
+        {
+            const std::vector<float>* w = P.get(p + ".up.weight");
+            const std::vector<float>* b = P.get(p + ".up.bias");
+            if (w && b) {
+                GemmW g;
+                g.N = 4 * out_c; g.Cin = in_c; g.taps = 1; g.K = in_c;
+                std::vector<float> Bm((size_t)g.N * g.K);
+                for (int i = 0; i < in_c; ++i)
+                    for (int co = 0; co < out_c; ++co)
+                        for (int ab = 0; ab < 4; ++ab)
+                            Bm[((size_t)ab * out_c + co) * g.K + i] = (*w)[((size_t)i * out_c + co) * 4 + ab];
+                if ((r = finish_gemm(e, g, Bm, *b))) return r;
+                e.gw[p + ".up"] = g;
+            }
+        }
+        if (e.has_gate(l)) {
+            const int fi = e.f_int(l);
+            GemmW g;
+            g.N = fi; g.Cin = in_c; g.taps = 1; g.K = in_c;       // K order = concat order [x | g]
+            std::vector<float> Bm((size_t)fi * g.K), bias(fi, 0.f), wpsi(fi);
+            bool ok = true;
+            if (e.pipeline()) {
+                const std::vector<float>* wg = P.get(p + ".att.Wg.0.weight");
+                const std::vector<float>* wx = P.get(p + ".att.Wx.0.weight");
+                const std::vector<float>* wq = P.get(p + ".att.psi.0.weight");
+                std::vector<double> sg, tg, sx, tx, sq, tq;
+                P.bn(p + ".att.Wg.1", fi, sg, tg);
+                P.bn(p + ".att.Wx.1", fi, sx, tx);
+                P.bn(p + ".att.psi.1", 1, sq, tq);
+                ok = wg && wx && wq;
+                if (ok) {
+                    for (int f = 0; f < fi; ++f) {
+                        bias[f] = (float)(tg[f] + tx[f]);
+                        wpsi[f] = (float)((double)(*wq)[f] * sq[0]);
+                        for (int k = 0; k < out_c; ++k) {
+                            Bm[(size_t)f * g.K + k] = (float)((double)(*wx)[(size_t)f * out_c + k] * sx[f]);
+                            Bm[(size_t)f * g.K + out_c + k] = (float)((double)(*wg)[(size_t)f * out_c + k] * sg[f]);
+                        }
+                    }
+                    g.scalar = (float)tq[0];
+                }
+            } else {
+                const std::vector<float>* wg = P.get(p + ".att.Wg.weight");
+                const std::vector<float>* wx = P.get(p + ".att.Wx.weight");
+                const std::vector<float>* wq = P.get(p + ".att.psi.1.weight");
+                const std::vector<float>* bq = P.get(p + ".att.psi.1.bias");
+                ok = wg && wx && wq && bq;
+                if (ok) {
+                    for (int f = 0; f < fi; ++f) {
+                        wpsi[f] = (*wq)[f];
+                        for (int k = 0; k < out_c; ++k) {
+                            Bm[(size_t)f * g.K + k] = (*wx)[(size_t)f * out_c + k];
+                            Bm[(size_t)f * g.K + out_c + k] = (*wg)[(size_t)f * out_c + k];
+                        }
+                    }
+                    g.scalar = (*bq)[0];
+                }
+            }
+            if (ok) {
+                if ((r = finish_gemm(e, g, Bm, bias))) return r;
+                if (upload(e, wpsi, &g.dvec) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "gate upload failed");
+                e.gw[p + ".att"] = g;
+            }
+        }
+        if ((r = prep_conv_bn(e, P, p + ".conv.0", p + ".conv.0.block.0.weight", p + ".conv.0.block.1", in_c, out_c, 9))) return r;
+        if ((r = prep_conv_bn(e, P, p + ".conv.1", p + ".conv.1.block.0.weight", p + ".conv.1.block.1", out_c, out_c, 9))) return r;
+    }
+    {
+        const std::vector<float>* w = P.get("out_conv.weight");
+        const std::vector<float>* b = P.get("out_conv.bias");
+        if (w && b && e.gw.count("u1.conv.1")) {
+            GemmW& g = e.gw["u1.conv.1"];
+            if (upload(e, *w, &g.dvec) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "out_conv upload failed");
+            g.scalar = (*b)[0];
+        }
+    }
+    if (!P.missing.empty()) return e.fail(AAU_ERR_WEIGHTS, "state_dict entry never loaded: " + P.missing);
+    e.committed = true;
+    return AAU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// plan building
+// ------------------------------------------------------------------------------------------------------------
+static int ilog2(int v) {
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
+}
+
+static bool encode_map(Engine& e, CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int swizzle_bytes) {
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = e.encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct Bump {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Bump(void* b) : base((uint8_t*)b) {}
+    uint8_t* take(size_t bytes) {
+        off = (off + 1023) & ~size_t(1023);
+        uint8_t* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+static View make_view(Bump& bump, int B, int H, int W, int C) {
+    View v;
+    v.B = B; v.H = H; v.W = W; v.C = C; v.ld = C; v.choff = 0;
+    v.p = bump.take(v.bytes());
+    return v;
+}
+static View sub_view(const View& v, int choff, int C) {
+    View s = v;
+    s.choff = v.choff + choff;
+    s.C = C;
+    return s;
+}
+
+// Builds one persistent-GEMM launch over up to 4 problems sharing input geometry, BN and KC.
+static int add_igemm(Engine& e, Plan& plan, const std::vector<ConvDesc>& descs, int patch_aux /*0 none,1 logits,2 psi3,3 psi2*/) {
+    IgemmParams P;
+    memset(&P, 0, sizeof(P));
+    const ConvDesc& d0 = descs[0];
+    const int Cin = d0.in.C, Ntot = d0.w->N;
+    if (Cin % 16) return e.fail(AAU_ERR_INVALID, "input channels must be a multiple of 16");
+    P.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
+    int BN = 0;
+    for (int cand = std::min(256, Ntot); cand >= 16; cand -= 16)
+        if (Ntot % cand == 0) { BN = cand; break; }
+    if (!BN) return e.fail(AAU_ERR_INVALID, "output channels must be a multiple of 16");
+    if (d0.epi == EPI_GATE || d0.epi == EPI_OUTCONV)
+        if (BN != Ntot) return e.fail(AAU_ERR_INVALID, "gate / out_conv epilogues need all channels in one tile");
+    P.BN = BN;
+    const bool conv3 = d0.w->taps == 9;
+    bool slab = conv3 && d0.dil == 1 && BN <= 128;
+    if (e.opt_amode == 0) slab = false;
+    if (e.opt_amode == 1 && conv3 && d0.dil == 1 && BN <= 128) slab = true;
+    P.amode = slab ? AMODE_SLAB : AMODE_TAP;
+    // tile shape: minimise padded pixels (and, for slabs, halo overhead)
+    const int H = d0.in.H, W = d0.in.W;
+    double best = 1e30;
+    for (int tw = 8; tw <= 128; tw <<= 1) {
+        const int th = 128 / tw;
+        if (slab && th < 4) continue;
+        double cost = (double)((H + th - 1) / th * th) * ((W + tw - 1) / tw * tw);
+        if (slab) cost *= 1.0 + 0.5 * 2.0 / th;     // halo rows cost bandwidth, not MMA time
+        if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
+    }
+    P.tw_shift = ilog2(P.TW);
+    const int swz = P.KC * 2;
+    P.b_sub_bytes = BN * swz;
+    if (slab) {
+        P.G = 3;
+        P.a_stage_bytes = ((P.TH + 2) * P.TW * swz + 1023) & ~1023;
+        P.stage_bytes = P.a_stage_bytes + 3 * P.b_sub_bytes;
+    } else {
+        const int sub_bytes = 128 * swz + P.b_sub_bytes;
+        const int sub_total = d0.w->taps * (Cin / P.KC);
+        P.G = std::max(1, std::min(std::min(4, sub_total), 40960 / sub_bytes));
+        P.a_stage_bytes = P.G * 128 * swz;
+        P.stage_bytes = P.G * sub_bytes;
+    }
+    P.stage_bytes = (P.stage_bytes + 1023) & ~1023;
+    const int smem_budget = 227 * 1024 - 2048;
+    P.nstages = std::min((int)IGEMM_MAX_STAGES, smem_budget / P.stage_bytes);
+    if (P.nstages < 2) return e.fail(AAU_ERR_INVALID, "pipeline stage does not fit in shared memory");
+    P.tmem_cols = 32;
+    while (P.tmem_cols < 2 * BN) P.tmem_cols <<= 1;
+    P.is_fp16 = e.is_fp16() ? 1 : 0;
+    P.err = e.d_err;
+    P.nprob = (int)descs.size();
+    int tile_begin = 0;
+    for (int i = 0; i < P.nprob; ++i) {
+        const ConvDesc& d = descs[i];
+        IgemmProblem& q = P.prob[i];
+        if (d.in.C != Cin || d.w->Cin != Cin || d.w->N != Ntot || d.in.H != H || d.in.W != W || d.in.B != d0.in.B ||
+            d.w->taps != d0.w->taps || (slab && d.dil != 1))
+            return e.fail(AAU_ERR_INVALID, "grouped problems must share geometry");
+        // activations: (C, W, H, B)
+        const uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)d.in.W, (uint64_t)d.in.H, (uint64_t)d.in.B};
+        const uint64_t astr[3] = {(uint64_t)d.in.ld * 2, (uint64_t)d.in.W * d.in.ld * 2, (uint64_t)d.in.H * d.in.W * d.in.ld * 2};
+        const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH + 2 : P.TH), 1u};
+        if (!encode_map(e, &q.tmA, d.in.p + (size_t)d.in.choff * 2, 4, adims, astr, abox, swz))
+            return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
+        const uint64_t bdims[2] = {(uint64_t)d.w->K, (uint64_t)d.w->N};
+        const uint64_t bstr[1] = {(uint64_t)d.w->K * 2};
+        const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)BN};
+        if (!encode_map(e, &q.tmB, d.w->dB, 2, bdims, bstr, bbox, swz))
+            return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight tensor");
+        q.bias = d.bias_img ? d.bias_img : d.w->dbias;
+        q.bias_img_stride = d.bias_img ? d.bias_img_stride : 0;
+        q.out = d.out.p;
+        q.vec = d.w->dvec;
+        q.aux = d.aux;
+        q.scalar = d.w->scalar;
+        q.H = H; q.W = W;
+        q.tiles_x = (W + P.TW - 1) / P.TW;
+        q.tiles_per_img = q.tiles_x * ((H + P.TH - 1) / P.TH);
+        q.m_tiles = d.in.B * q.tiles_per_img;
+        q.n_tiles = Ntot / BN;
+        q.tile_begin = tile_begin;
+        tile_begin += q.m_tiles * q.n_tiles;
+        q.taps = d.w->taps; q.dil = d.dil; q.nchunk = Cin / P.KC;
+        q.epi = d.epi; q.relu = d.relu;
+        q.outH = d.out.H; q.outW = d.out.W; q.out_ld = d.out.ld; q.out_choff = d.out.choff;
+        q.convt_cout = d.convt_cout;
+        q.gate_C = d.out.C; q.gate_plus_x = d.gate_plus_x;
+    }
+    P.total_tiles = tile_begin;
+    const int grid = std::min(P.total_tiles, e.num_sms);
+    const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
+    plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
+        IgemmParams Q = P;
+        if (patch_aux == 1) Q.prob[0].aux = a.logits;
+        if (patch_aux == 2) Q.prob[0].aux = a.psi3;
+        if (patch_aux == 3) Q.prob[0].aux = a.psi2;
+        igemm_tc_kernel<<<grid, IGEMM_THREADS, smem, a.stream>>>(Q);
+        return cudaGetLastError();
+    });
+    return AAU_OK;
+}
+
+static int ew_grid(const Engine& e, long long work_items, int block) {
+    long long g = (work_items + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, (long long)e.num_sms * 8));
+}
+
+static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size_t* need_bytes) {
+    plan.B = B; plan.H = H; plan.W = W; plan.ws = ws;
+    Bump bump(ws);
+    const bool dry = ws == nullptr;
+    const int c = e.cfg.base_c, f16 = e.is_fp16() ? 1 : 0;
+    int ch[6], Hs[6], Ws[6];
+    Hs[1] = H; Ws[1] = W;
+    for (int l = 1; l <= 4; ++l) { ch[l] = c << (l - 1); Hs[l + 1] = Hs[l] / 2; Ws[l + 1] = Ws[l] / 2; }
+    if (Hs[5] < 1 || Ws[5] < 1) return e.fail(AAU_ERR_INVALID, "H and W must be at least 16");
+    View ta[5], cat[5], pl[5], ua[5], dd[5], tmpg[5];
+    for (int l = 1; l <= 4; ++l) {
+        ta[l] = make_view(bump, B, Hs[l], Ws[l], ch[l]);
+        cat[l] = make_view(bump, B, Hs[l], Ws[l], 2 * ch[l]);
+        pl[l] = make_view(bump, B, Hs[l + 1], Ws[l + 1], ch[l]);
+        ua[l] = make_view(bump, B, Hs[l], Ws[l], ch[l]);
+        if (l > 1) dd[l] = make_view(bump, B, Hs[l], Ws[l], ch[l]);
+        if (2 * Hs[l + 1] != Hs[l] || 2 * Ws[l + 1] != Ws[l]) tmpg[l] = make_view(bump, B, 2 * Hs[l + 1], 2 * Ws[l + 1], ch[l]);
+    }
+    const int oc = 16 * c;
+    View asppcat, bo = make_view(bump, B, Hs[5], Ws[5], oc);
+    float* bias_img = nullptr;
+    if (e.has_aspp()) {
+        asppcat = make_view(bump, B, Hs[5], Ws[5], 4 * oc);
+        bias_img = (float*)bump.take((size_t)B * oc * sizeof(float));
+    }
+    *need_bytes = bump.off + 1024;
+    if (dry) return AAU_OK;
+
+    plan.named["x1"] = sub_view(cat[1], 0, ch[1]);
+    plan.named["x2"] = sub_view(cat[2], 0, ch[2]);
+    plan.named["x3"] = sub_view(cat[3], 0, ch[3]);
+    plan.named["x4"] = sub_view(cat[4], 0, ch[4]);
+    plan.named["d1.0"] = ta[1];
+    plan.named["p4"] = pl[4];
+    plan.named["bridge"] = bo;
+    plan.named["d4"] = dd[4];
+    plan.named["d3"] = dd[3];
+    plan.named["d2"] = dd[2];
+    plan.named["g4"] = sub_view(cat[4], ch[4], ch[4]);
+    plan.named["g3"] = sub_view(cat[3], ch[3], ch[3]);
+    plan.named["g2"] = sub_view(cat[2], ch[2], ch[2]);
+    plan.named["g1"] = sub_view(cat[1], ch[1], ch[1]);
+    plan.named["u4a"] = ua[4];
+    plan.named["u1a"] = ua[1];
+    if (e.has_aspp()) plan.named["asppcat"] = asppcat;
+
+    int r;
+    auto conv = [&](const std::string& name, const View& in, const View& out, int dil = 1) -> int {
+        ConvDesc d;
+        d.w = &e.gw.at(name);
+        d.in = in; d.out = out; d.dil = dil; d.epi = EPI_STORE; d.relu = 1;
+        return add_igemm(e, plan, {d}, 0);
+    };
+    auto pool = [&](const View& in, const View& out) {
+        const long long items = (long long)in.B * (in.H / 2) * (in.W / 2) * (in.C / 8);
+        const int grid = ew_grid(e, items, 256);
+        plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+            maxpool2x2_kernel<<<grid, 256, 0, a.stream>>>(in.p, in.ld, in.choff, in.B, in.H, in.W, in.C, out.p, f16);
+            return cudaGetLastError();
+        });
+    };
+    // ---- encoder
+    {
+        const View o = ta[1];
+        const float* w = e.d_stem_w;
+        const float* b = e.d_stem_b;
+        const int grid = ew_grid(e, (long long)B * H * W, 256);
+        const size_t smem = (size_t)10 * c * sizeof(float);
+        plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+            stem_conv3x3_kernel<<<grid, 256, smem, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, f16);
+            return cudaGetLastError();
+        });
+    }
+    if ((r = conv("d1.1", ta[1], sub_view(cat[1], 0, ch[1])))) return r;
+    for (int l = 2; l <= 4; ++l) {
+        pool(sub_view(cat[l - 1], 0, ch[l - 1]), pl[l - 1]);
+        const std::string p = "d" + std::to_string(l);
+        if ((r = conv(p + ".0", pl[l - 1], ta[l]))) return r;
+        if ((r = conv(p + ".1", ta[l], sub_view(cat[l], 0, ch[l])))) return r;
+    }
+    pool(sub_view(cat[4], 0, ch[4]), pl[4]);
+    // ---- bridge
+    if (e.has_aspp()) {
+        {
+            const View in = pl[4];
+            const int HW = in.H * in.W, Cin = in.C;
+            const float *pT = e.d_poolT, *pb = e.d_poolb, *jT = e.d_projT, *jb = e.d_projb;
+            const int pairs = Cin / 2, lanes = std::max(1, 512 / pairs);
+            const size_t smem = ((size_t)lanes * Cin + Cin + oc) * sizeof(float);
+            plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+                aspp_pool_bias_kernel<<<in.B, 512, smem, a.stream>>>(in.p, HW, Cin, oc, pT, pb, jT, jb, bias_img, f16);
+                return cudaGetLastError();
+            });
+        }
+        // the four conv branches in ONE launch, each writing its slice of the concatenated tensor
+        const int rates[4] = {1, 6, 12, 18};
+        // the 1x1 branch has a different K extent, so it gets its own launch; the three dilated branches share one
+        {
+            ConvDesc d;
+            d.w = &e.gw.at("aspp.0");
+            d.in = pl[4]; d.out = sub_view(asppcat, 0, oc); d.epi = EPI_STORE; d.relu = 1;
+            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+        }
+        std::vector<ConvDesc> dil3;
+        for (int i = 1; i <= 3; ++i) {
+            ConvDesc d;
+            d.w = &e.gw.at("aspp." + std::to_string(i));
+            d.in = pl[4]; d.out = sub_view(asppcat, i * oc, oc); d.dil = rates[i]; d.epi = EPI_STORE; d.relu = 1;
+            dil3.push_back(d);
+        }
+        if ((r = add_igemm(e, plan, dil3, 0))) return r;
+        {
+            ConvDesc d;
+            d.w = &e.gw.at("aspp.project");
+            d.in = asppcat; d.out = bo; d.epi = EPI_STORE; d.relu = 1;
+            d.bias_img = bias_img; d.bias_img_stride = oc;
+            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+        }
+    } else {
+        if ((r = conv("bridge.0", pl[4], bo))) return r;
+    }
+    // ---- decoder
+    for (int l = 4; l >= 1; --l) {
+        const std::string p = "u" + std::to_string(l);
+        const View gin = (l == 4) ? bo : dd[l + 1];
+        const View gdst = sub_view(cat[l], ch[l], ch[l]);
+        const bool fix = tmpg[l].p != nullptr;
+        {
+            ConvDesc d;
+            d.w = &e.gw.at(p + ".up");
+            d.in = gin; d.out = fix ? tmpg[l] : gdst; d.epi = EPI_CONVT; d.relu = 0; d.convt_cout = ch[l];
+            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+        }
+        if (fix) {
+            const View in = tmpg[l];
+            const long long items = (long long)B * Hs[l] * Ws[l] * (ch[l] / 8);
+            const int grid = ew_grid(e, items, 256);
+            plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+                resize_bilinear_kernel<<<grid, 256, 0, a.stream>>>(in.p, in.H, in.W, in.C, gdst.p, gdst.H, gdst.W, gdst.ld, gdst.choff, in.B, f16);
+                return cudaGetLastError();
+            });
+        }
+        if (e.has_gate(l)) {
+            ConvDesc d;
+            d.w = &e.gw.at(p + ".att");
+            d.in = sub_view(cat[l], 0, 2 * ch[l]);
+            d.out = sub_view(cat[l], 0, ch[l]);
+            d.epi = EPI_GATE; d.relu = 1;
+            d.gate_plus_x = e.pipeline() ? 0 : 1;
+            const int patch = e.pipeline() ? 0 : (l == 4 ? 2 : (l == 3 ? 3 : 0));
+            if ((r = add_igemm(e, plan, {d}, patch))) return r;
+        }
+        if ((r = conv(p + ".conv.0", sub_view(cat[l], 0, 2 * ch[l]), ua[l]))) return r;
+        if (l > 1) {
+            if ((r = conv(p + ".conv.1", ua[l], dd[l]))) return r;
+        } else {
+            ConvDesc d;
+            d.w = &e.gw.at("u1.conv.1");
+            d.in = ua[1]; d.out = ua[1]; d.epi = EPI_OUTCONV; d.relu = 1;
+            if ((r = add_igemm(e, plan, {d}, 1))) return r;
+        }
+    }
+    return AAU_OK;
+}
+
+}  // namespace aau
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+using namespace aau;
+struct aau_handle {
+    Engine e;
+};
+
+extern "C" {
+
+int aau_create(const aau_config* cfg, int device, aau_handle** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return AAU_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->in_channels != 1 || cfg->num_classes != 1) { g_create_error = "only in_channels=1, num_classes=1 are supported"; return AAU_ERR_INVALID; }
+    if (cfg->base_c < 16 || cfg->base_c % 16) { g_create_error = "base_c must be a positive multiple of 16"; return AAU_ERR_INVALID; }
+    if (cfg->variant != AAU_VARIANT_PIPELINE && cfg->variant != AAU_VARIANT_ABLATION) { g_create_error = "unknown variant"; return AAU_ERR_INVALID; }
+    if (cfg->act_dtype != AAU_ACT_BF16 && cfg->act_dtype != AAU_ACT_FP16) { g_create_error = "unknown act_dtype"; return AAU_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device: libaau has no CPU fallback";
+        return AAU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return AAU_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_error = "cudaGetDeviceProperties failed"; return AAU_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "libaau is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return AAU_ERR_INVALID;
+    }
+    auto* h = new aau_handle();
+    Engine& e = h->e;
+    e.cfg = *cfg;
+    e.device = device;
+    e.num_sms = prop.multiProcessorCount;
+    build_keys(e);
+    cudaSetDevice(device);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        g_create_error = "cuTensorMapEncodeTiled not available from the driver";
+        delete h;
+        return AAU_ERR_CUDA;
+    }
+    e.encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    if (cudaMalloc(&e.d_err, 256) != cudaSuccess || cudaMemset(e.d_err, 0, 256) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed";
+        delete h;
+        return AAU_ERR_CUDA;
+    }
+    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) {
+        g_create_error = "cannot raise the dynamic shared memory limit";
+        delete h;
+        return AAU_ERR_CUDA;
+    }
+    *out = h;
+    return AAU_OK;
+}
+
+int aau_destroy(aau_handle* h) {
+    if (!h) return AAU_OK;
+    cudaSetDevice(h->e.device);
+    for (void* p : h->e.dev_allocs) cudaFree(p);
+    if (h->e.d_err) cudaFree(h->e.d_err);
+    delete h;
+    return AAU_OK;
+}
+
+const char* aau_last_error(const aau_handle* h) { return h ? h->e.err.c_str() : g_create_error.c_str(); }
+
+int aau_num_keys(const aau_handle* h) { return h ? (int)h->e.keys.size() : 0; }
+const char* aau_key_name(const aau_handle* h, int i) {
+    return (h && i >= 0 && i < (int)h->e.keys.size()) ? h->e.keys[i].name.c_str() : "";
+}
+int64_t aau_key_numel(const aau_handle* h, int i) { return (h && i >= 0 && i < (int)h->e.keys.size()) ? h->e.keys[i].numel : 0; }
+
+int aau_load_tensor(aau_handle* h, const char* key, const float* data, int64_t numel) {
+    if (!h || !key || !data) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    std::string k(key);
+    // legacy checkpoints spell the gate convs W_g / W_x (attention_aspp_unet_pipeline_stage.py:134-141)
+    for (const char* pat : {".W_g.", ".W_x."}) {
+        size_t pos = k.find(pat);
+        if (pos != std::string::npos) k.replace(pos, 5, pat[3] == 'g' ? ".Wg." : ".Wx.");
+    }
+    for (const KeySpec& s : e.keys) {
+        if (s.name == k) {
+            if (s.numel != numel) return e.fail(AAU_ERR_WEIGHTS, "size mismatch for " + k);
+            e.host[k].assign(data, data + numel);
+            e.committed = false;
+            return AAU_OK;
+        }
+    }
+    ++e.unexpected;
+    return AAU_OK;
+}
+
+int aau_commit_weights(aau_handle* h) {
+    if (!h) return AAU_ERR_INVALID;
+    cudaSetDevice(h->e.device);
+    return commit_weights(h->e);
+}
+
+int aau_missing_count(const aau_handle* h) {
+    if (!h) return 0;
+    int n = 0;
+    for (const KeySpec& s : h->e.keys) n += h->e.host.count(s.name) ? 0 : 1;
+    return n;
+}
+int aau_unexpected_count(const aau_handle* h) { return h ? h->e.unexpected : 0; }
+
+size_t aau_workspace_bytes(const aau_handle* h, int B, int H, int W) {
+    if (!h || B < 1 || H < 16 || W < 16) return 0;
+    Engine& e = const_cast<Engine&>(h->e);
+    Plan tmp;
+    size_t need = 0;
+    if (build_plan(e, tmp, B, H, W, nullptr, &need) != AAU_OK) return 0;
+    return need;
+}
+
+int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, float* logits, float* psi3, float* psi2,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!e.committed) return e.fail(AAU_ERR_STATE, "aau_forward before aau_commit_weights");
+    if (!x || !logits || !workspace || B < 1 || H < 16 || W < 16) return e.fail(AAU_ERR_INVALID, "bad forward arguments");
+    if (x_dtype != AAU_X_F32 && x_dtype != AAU_X_U8) return e.fail(AAU_ERR_INVALID, "unknown x_dtype");
+    if ((uintptr_t)workspace & 255) return e.fail(AAU_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    cudaSetDevice(e.device);
+    Plan* plan = nullptr;
+    for (auto& p : e.plans)
+        if (p->B == B && p->H == H && p->W == W && p->ws == workspace) plan = p.get();
+    if (!plan) {
+        size_t need = 0;
+        {
+            Plan dry;
+            int r = build_plan(e, dry, B, H, W, nullptr, &need);
+            if (r) return r;
+        }
+        if (workspace_bytes < need) return e.fail(AAU_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+        auto np = std::make_unique<Plan>();
+        int r = build_plan(e, *np, B, H, W, workspace, &need);
+        if (r) return r;
+        if (e.plans.size() >= 8) e.plans.erase(e.plans.begin());
+        e.plans.push_back(std::move(np));
+        plan = e.plans.back().get();
+    }
+    FwdArgs a{x, x_dtype, logits, psi3, psi2, (cudaStream_t)stream};
+    int n = 0;
+    for (auto& op : plan->ops) {
+        cudaError_t r = op(a);
+        if (r != cudaSuccess) return e.fail(AAU_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(r));
+        ++n;
+    }
+    e.last_launches = n;
+    return AAU_OK;
+}
+
+int aau_frame_scores(aau_handle* h, const float* logits, int input_kind, int N, int H, int W, float prob_thr, int32_t* areas,
+                     int32_t* best, uint8_t* mask, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!logits || !areas || N < 1 || H < 1 || W < 1) return e.fail(AAU_ERR_INVALID, "bad frame_scores arguments");
+    cudaSetDevice(e.device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AAU_CUDA(cudaMemsetAsync(areas, 0, (size_t)N * sizeof(int32_t), s));
+    const int HW = H * W;
+    const int gx = std::max(1, std::min(64, (HW / 4 + 255) / 256));
+    frame_area_kernel<<<dim3(gx, N), 256, 0, s>>>(logits, input_kind == AAU_IN_PROB ? 1 : 0, HW, prob_thr, areas, mask);
+    AAU_CUDA(cudaGetLastError());
+    if (best) {
+        area_argmax_kernel<<<1, 1024, 0, s>>>(areas, N, best);
+        AAU_CUDA(cudaGetLastError());
+    }
+    return AAU_OK;
+}
+
+int aau_device_fault(aau_handle* h) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    cudaSetDevice(e.device);
+    cudaError_t r = cudaDeviceSynchronize();
+    int flag = 0;
+    cudaError_t r2 = cudaMemcpy(&flag, e.d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (r != cudaSuccess || r2 != cudaSuccess)
+        return e.fail(AAU_ERR_DEVICE, std::string("device error: ") + cudaGetErrorString(r != cudaSuccess ? r : r2) + " (pipeline flag " + std::to_string(flag) + ")");
+    if (flag) return e.fail(AAU_ERR_DEVICE, "kernel pipeline wait timed out, code " + std::to_string(flag));
+    return AAU_OK;
+}
+
+int aau_num_launches(const aau_handle* h) { return h ? h->e.last_launches : 0; }
+
+int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff) {
+    if (!h || !name) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (e.plans.empty()) return e.fail(AAU_ERR_STATE, "no forward has run yet");
+    Plan& p = *e.plans.back();
+    auto it = p.named.find(name);
+    if (it == p.named.end() || !it->second.p) return e.fail(AAU_ERR_INVALID, std::string("unknown tensor ") + name);
+    const View& v = it->second;
+    if (ptr) *ptr = v.p;
+    if (B) *B = v.B;
+    if (H) *H = v.H;
+    if (W) *W = v.W;
+    if (C) *C = v.C;
+    if (ld) *ld = v.ld;
+    if (choff) *choff = v.choff;
+    return AAU_OK;
+}
+
+int aau_set_option(aau_handle* h, const char* name, int value) {
+    if (!h || !name) return AAU_ERR_INVALID;
+    if (std::string(name) == "amode") {
+        h->e.opt_amode = value;
+        h->e.plans.clear();
+        return AAU_OK;
+    }
+    return h->e.fail(AAU_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+}  // extern "C"

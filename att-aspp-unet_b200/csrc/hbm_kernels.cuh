@@ -1,0 +1,263 @@
+// HBM-bound kernels of the AttentionASPPUNet forward: everything that is not a tensor-core GEMM.
+// All activations are NHWC with 16-bit elements (bf16 default, fp16 optional); a tensor inside a concatenated
+// buffer is addressed by (pixel stride `ld` in channels, channel offset `choff`).  Every thread moves 16-byte
+// vectors (8 channels) and neighbouring threads touch neighbouring addresses.
+#pragma once
+#include "igemm_tc.cuh"
+
+namespace aau {
+
+// ---------------------------------------------------------------------------------------------------------
+// d1.0: Conv2d(1 -> C, 3x3, pad 1, no bias) + BN(folded) + ReLU straight from the input frame.
+// (attention_aspp_unet_pipeline_stage.py:114 first ConvBNReLU; input normalisation `u8/255` as
+//  model_attention_aspp.py:17.)  K = 9 is far too small for the tensor cores: one thread per pixel, fp32 FMAs,
+// weights broadcast from shared memory, the C output channels of a pixel written as 16-byte vectors.
+// x_dtype: 0 = float32 [B,1,H,W] (already in [0,1]), 1 = uint8 [B,H,W] (normalised here as float(u8)/255.0f).
+__global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restrict__ x, int x_dtype, int B, int H, int W,
+                                                           const float* __restrict__ w9c,   // [9][C], BN scale folded in
+                                                           const float* __restrict__ bias,  // [C]
+                                                           uint8_t* __restrict__ out, int out_ld, int out_choff, int C, int is_fp16) {
+    extern __shared__ float s_w[];      // [9][C] weights then [C] bias
+    for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) s_w[i] = i < 9 * C ? w9c[i] : bias[i - 9 * C];
+    __syncthreads();
+    const long long npix = (long long)B * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        const int xw = (int)(p % W);
+        const long long t = p / W;
+        const int y = (int)(t % H);
+        const long long b = t / H;
+        float v[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = y + ky - 1, xx = xw + kx - 1;
+                float val = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    const long long idx = (b * H + yy) * W + xx;
+                    val = x_dtype == 0 ? __ldg((const float*)x + idx) : (float)__ldg((const uint8_t*)x + idx) / 255.0f;
+                }
+                v[ky * 3 + kx] = val;
+            }
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)p * out_ld + out_choff) * 2);
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = s_w[9 * C + c0 + i];
+#pragma unroll
+            for (int tpi = 0; tpi < 9; ++tpi)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[tpi], s_w[tpi * C + c0 + i], acc[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+            dst[c0 >> 3] = make_uint4(pack2(acc[0], acc[1], is_fp16), pack2(acc[2], acc[3], is_fp16),
+                                      pack2(acc[4], acc[5], is_fp16), pack2(acc[6], acc[7], is_fp16));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MaxPool2d(2) with floor semantics (attention_aspp_unet_pipeline_stage.py:115-118): the last odd row/column is
+// never read.  One thread = one output pixel x 8 channels.
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_fp16) {
+    if (is_fp16) {
+        __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int f) {
+    return make_uint4(max2(a.x, b.x, f), max2(a.y, b.y, f), max2(a.z, b.z, f), max2(a.w, b.w, f));
+}
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const uint8_t* __restrict__ in, int in_ld, int in_choff, int B, int H, int W, int C,
+                                                         uint8_t* __restrict__ out, int is_fp16) {
+    const int OH = H >> 1, OW = W >> 1, CV = C >> 3;
+    const long long total = (long long)B * OH * OW * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long t = i / CV;
+        const int ox = (int)(t % OW);
+        t /= OW;
+        const int oy = (int)(t % OH);
+        const long long b = t / OH;
+        const uint8_t* p00 = in + ((((size_t)b * H + 2 * oy) * W + 2 * ox) * in_ld + in_choff + cv * 8) * 2;
+        const size_t px = (size_t)in_ld * 2, row = (size_t)W * in_ld * 2;
+        const uint4 a = __ldg((const uint4*)p00), bq = __ldg((const uint4*)(p00 + px));
+        const uint4 c = __ldg((const uint4*)(p00 + row)), d = __ldg((const uint4*)(p00 + row + px));
+        *reinterpret_cast<uint4*>(out + (size_t)i * 16) = max8(max8(a, bq, is_fp16), max8(c, d, is_fp16), is_fp16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ASPP image-pooling branch folded into a per-image bias of the project conv (SURVEY.md identity i2;
+// attention_aspp_unet_pipeline_stage.py:75-77,80-83): bilinear up-sampling of a 1x1 map is a broadcast, so
+//   bias_img[b][o] = sum_j Wproj[o][4*Co + j] * relu(sum_i Wpool[j][i] * mean_hw(x[b,:,:,i]) + bpool[j]) + bproj[o].
+// One block per frame.  Phase 1 reduces the frame's pixels per channel with coalesced 4-byte (2-channel) loads
+// and a shared-memory tree across pixel lanes; phases 2/3 are two small mat-vecs on transposed fp32 weights so
+// that consecutive threads read consecutive addresses.
+__global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const uint8_t* __restrict__ x, int HW, int Cin, int Cout,
+                                                             const float* __restrict__ wpoolT,   // [Cin][Cout], BN folded
+                                                             const float* __restrict__ bpool,    // [Cout]
+                                                             const float* __restrict__ wprojT,   // [Cout][Cout] pool slice of project, BN folded
+                                                             const float* __restrict__ bproj,    // [Cout]
+                                                             float* __restrict__ bias_img, int is_fp16) {
+    extern __shared__ float s_buf[];                 // [lanes][Cin] partial sums, then mean[Cin] | v[Cout]
+    const int b = blockIdx.x;
+    const int pairs = Cin >> 1;
+    const int lanes = blockDim.x / pairs;            // pixel lanes
+    const int pl = threadIdx.x / pairs, cp = threadIdx.x % pairs;
+    float s0 = 0.f, s1 = 0.f;
+    if (pl < lanes) {
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(x + (size_t)b * HW * Cin * 2) + cp;
+        for (int p = pl; p < HW; p += lanes) {
+            const float2 f = unpack2(__ldg(base + (size_t)p * pairs), is_fp16);
+            s0 += f.x;
+            s1 += f.y;
+        }
+        s_buf[pl * Cin + 2 * cp] = s0;
+        s_buf[pl * Cin + 2 * cp + 1] = s1;
+    }
+    __syncthreads();
+    float* mean = s_buf + lanes * Cin;
+    float* v = mean + Cin;
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += s_buf[l * Cin + c];
+        mean[c] = s / (float)HW;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < Cout; o += blockDim.x) {
+        float s = bpool[o];
+        for (int i = 0; i < Cin; ++i) s = fmaf(wpoolT[(size_t)i * Cout + o], mean[i], s);
+        v[o] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < Cout; o += blockDim.x) {
+        float s = bproj[o];
+        for (int j = 0; j < Cout; ++j) s = fmaf(wprojT[(size_t)j * Cout + o], v[j], s);
+        bias_img[(size_t)b * Cout + o] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// F.interpolate(mode="bilinear", align_corners=False) from (IH, IW) to (OH, OW) -- the decoder's fix-up when the
+// floor-pooled skip is one row/column larger than the transposed-conv output
+// (attention_aspp_unet_pipeline_stage.py:106-107).  Index arithmetic follows ATen's upsample_bilinear2d:
+// scale = in/out, src = max(0, scale*(dst+0.5)-0.5), i0 = floor(src), i1 = min(i0+1, in-1), w1 = src-i0.
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __restrict__ in, int IH, int IW, int C,
+                                                              uint8_t* __restrict__ out, int OH, int OW, int out_ld, int out_choff,
+                                                              int B, int is_fp16) {
+    const int CV = C >> 3;
+    const float sh = (float)IH / (float)OH, sw = (float)IW / (float)OW;
+    const long long total = (long long)B * OH * OW * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long t = i / CV;
+        const int ox = (int)(t % OW);
+        t /= OW;
+        const int oy = (int)(t % OH);
+        const long long b = t / OH;
+        float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
+        const float wy1 = fy - (float)y0, wx1 = fx - (float)x0;
+        const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+        const uint8_t* base = in + (size_t)b * IH * IW * C * 2 + (size_t)cv * 16;
+        const uint4 q00 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x0) * C * 2));
+        const uint4 q01 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x1) * C * 2));
+        const uint4 q10 = __ldg((const uint4*)(base + ((size_t)y1 * IW + x0) * C * 2));
+        const uint4 q11 = __ldg((const uint4*)(base + ((size_t)y1 * IW + x1) * C * 2));
+        const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+        const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 v00 = unpack2(a00[k], is_fp16), v01 = unpack2(a01[k], is_fp16);
+            const float2 v10 = unpack2(a10[k], is_fp16), v11 = unpack2(a11[k], is_fp16);
+            const float rx = wy0 * (wx0 * v00.x + wx1 * v01.x) + wy1 * (wx0 * v10.x + wx1 * v11.x);
+            const float ry = wy0 * (wx0 * v00.y + wx1 * v01.y) + wy1 * (wx0 * v10.y + wx1 * v11.y);
+            o[k] = pack2(rx, ry, is_fp16);
+        }
+        uint8_t* dst = out + ((((size_t)b * OH + oy) * OW + ox) * out_ld + out_choff + cv * 8) * 2;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Selection head: per-frame sigmoid / threshold / mask area, then first-max argmax over frames
+// (model_attention_aspp.py:54 sigmoid, :71 `prob > 0.05`, :74 / :94 `sum((1,2)).argmax()`).
+// Each thread reads float4 logits, evaluates sigmoid in fp32 exactly as `1/(1+exp(-x))`, counts, then the counts
+// are reduced with warp shuffles, one shared-memory hop per block and ONE integer atomic per block, so the result
+// is exact and order independent.  The optional mask output is the uint8 {0,1} volume the reference builds.
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int above(float v, float thr, int is_prob) {
+    return (is_prob ? v : 1.f / (1.f + expf(-v))) > thr;
+}
+__global__ void __launch_bounds__(256) frame_area_kernel(const float* __restrict__ logits, int is_prob, int HW, float thr,
+                                                         int* __restrict__ areas, uint8_t* __restrict__ mask) {
+    const int frame = blockIdx.y;
+    const float* src = logits + (size_t)frame * HW;
+    uint8_t* m = mask ? mask + (size_t)frame * HW : nullptr;
+    int cnt = 0;
+    const bool vec_ok = ((HW & 3) == 0) && ((((size_t)frame * HW) & 3) == 0);
+    if (vec_ok) {
+        const int n4 = HW >> 2;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+            const int b0 = above(v.x, thr, is_prob), b1 = above(v.y, thr, is_prob);
+            const int b2 = above(v.z, thr, is_prob), b3 = above(v.w, thr, is_prob);
+            cnt += b0 + b1 + b2 + b3;
+            if (m) reinterpret_cast<uint32_t*>(m)[i] = (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)b3 << 24);
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+            const int b0 = above(__ldg(src + i), thr, is_prob);
+            cnt += b0;
+            if (m) m[i] = (uint8_t)b0;
+        }
+    }
+    __shared__ int s_part[8];
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && v) atomicAdd(areas + frame, v);
+    }
+}
+
+// first index of the maximum area (numpy argmax tie-break); out[0] = index, out[1] = area at that index
+__global__ void __launch_bounds__(1024) area_argmax_kernel(const int* __restrict__ areas, int n, int* __restrict__ out) {
+    int best = -1, best_i = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int a = areas[i];
+        if (a > best) { best = a; best_i = i; }       // strided scan keeps the smallest index per thread on ties
+    }
+    __shared__ int s_v[32], s_i[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = best_i; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        best = threadIdx.x < nw ? s_v[threadIdx.x] : -1;
+        best_i = threadIdx.x < nw ? s_i[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (threadIdx.x == 0) { out[0] = best_i; out[1] = best; }
+    }
+}
+
+}  // namespace aau

@@ -1,0 +1,121 @@
+/* libaau -- C ABI of the B200-native AttentionASPPUNet inference engine.
+ *
+ * The reference (vivi-git188/ATT-ASPP-UNET) is pure Python and has no FFI of its own: its boundary for this hot
+ * path is the duck-typed torch.nn.Module `AttentionASPPUNet` plus two numpy helpers.  Every entry point below
+ * replaces one of those reference interfaces (file:line relative to /root/reference) and is what the Python
+ * host layer in att-aspp-unet_b200/ binds with ctypes.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns 0 on success and a
+ * negative aau_status on failure, never throws or aborts; `aau_last_error` gives the message.  All device work
+ * is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = legacy default stream) with no
+ * hidden synchronisation unless stated.  The caller owns input / output / workspace buffers (device memory);
+ * the library owns its packed weights.  One handle per (device, host thread): there is no global mutable state.
+ */
+#ifndef AAU_H_
+#define AAU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aau_handle aau_handle;
+
+typedef enum {
+    AAU_OK = 0,
+    AAU_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    AAU_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+    AAU_ERR_STATE = -3,       /* call order (e.g. forward before weights were committed) */
+    AAU_ERR_WEIGHTS = -4,     /* missing / mis-shaped state_dict entry */
+    AAU_ERR_WORKSPACE = -5,   /* workspace too small or misaligned */
+    AAU_ERR_DEVICE = -6       /* a kernel reported a pipeline fault (see aau_device_fault) */
+} aau_status;
+
+enum { AAU_VARIANT_PIPELINE = 0, AAU_VARIANT_ABLATION = 1 };
+enum { AAU_ACT_BF16 = 0, AAU_ACT_FP16 = 1 };
+enum { AAU_X_F32 = 0, AAU_X_U8 = 1 };
+enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1 };
+
+/* Constructor arguments.
+ * Replaces AttentionASPPUNet.__init__(in_channels=1, num_classes=1, base_c=32)
+ *   attention_aspp_unet_pipeline_stage.py:111-122                       (variant = AAU_VARIANT_PIPELINE)
+ * and AttentionASPPUNet.__init__(..., use_att, use_aspp, att_depth)
+ *   test_ablation.py:168-203                                            (variant = AAU_VARIANT_ABLATION). */
+typedef struct {
+    int32_t in_channels;   /* must be 1 */
+    int32_t num_classes;   /* must be 1 */
+    int32_t base_c;        /* multiple of 16 (reference uses 16, 32, 48) */
+    int32_t variant;       /* AAU_VARIANT_* */
+    int32_t use_att;       /* ablation only */
+    int32_t use_aspp;      /* ablation only */
+    int32_t att_depth;     /* ablation only */
+    int32_t act_dtype;     /* AAU_ACT_*: storage type of activations / packed weights (accumulation is fp32) */
+} aau_config;
+
+/* Replaces `AttentionASPPUNet(...).to(device)` (model_attention_aspp.py:36). */
+int aau_create(const aau_config* cfg, int device, aau_handle** out);
+int aau_destroy(aau_handle* h);
+/* Message of the last failure on this handle (or on creation when h == NULL).  Never NULL. */
+const char* aau_last_error(const aau_handle* h);
+
+/* Replaces `load_state_dict(sd, strict=False)` (model_attention_aspp.py:37,
+ * attention_aspp_unet_pipeline_stage.py:134-141): feed every floating-point state_dict entry by its reference
+ * key (fp32, contiguous, host memory), then commit.  Unknown keys are ignored and reported through
+ * aau_unexpected_count (strict=False semantics; the legacy spellings `.W_g.` / `.W_x.` are renamed as the
+ * reference does).  Keys never loaded are counted by aau_missing_count: BatchNorm entries then take the module
+ * defaults (gamma 1, beta 0, mean 0, var 1), while a missing convolution weight / bias makes the commit fail
+ * with AAU_ERR_WEIGHTS (the host layer always feeds its own initialised parameters).  aau_commit_weights folds BatchNorm (eps 1e-5) in fp32, rounds ONCE to the
+ * activation dtype, re-lays weights K-major for the tensor cores and uploads them (synchronous). */
+int aau_load_tensor(aau_handle* h, const char* key, const float* data, int64_t numel);
+int aau_commit_weights(aau_handle* h);
+int aau_missing_count(const aau_handle* h);
+int aau_unexpected_count(const aau_handle* h);
+/* Number of state_dict keys this configuration owns and the i-th key / its element count (layout contract,
+ * SURVEY.md section 8 a9). */
+int aau_num_keys(const aau_handle* h);
+const char* aau_key_name(const aau_handle* h, int i);
+int64_t aau_key_numel(const aau_handle* h, int i);
+
+/* Bytes of device scratch `aau_forward` needs for a batch of B frames of H x W (0 on invalid arguments). */
+size_t aau_workspace_bytes(const aau_handle* h, int B, int H, int W);
+
+/* Replaces `AttentionASPPUNet.forward(x)` (attention_aspp_unet_pipeline_stage.py:123-127; ablation twin
+ * test_ablation.py:205-218).
+ *   x       : device, [B,1,H,W] float32 in [0,1] (AAU_X_F32) or [B,H,W] uint8 (AAU_X_U8, normalised as
+ *             float(u8)/255.0f like model_attention_aspp.py:17)
+ *   logits  : device, float32 [B,1,H,W]
+ *   psi3/psi2 : ablation variant only, device float32 [B,1,H/8,W/8] and [B,1,H/4,W/4]; may be NULL
+ *   workspace : device, 256-byte aligned, at least aau_workspace_bytes(h,B,H,W)
+ * H, W >= 16.  Asynchronous on `stream`. */
+int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, float* logits, float* psi3,
+                float* psi2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the selection head: `torch.sigmoid(...)` (model_attention_aspp.py:54), `(prob > thr)` (:71),
+ * `bin_.sum((1,2)).argmax()` (:74) and `select_fetal_abdomen_mask_and_frame` (:91-97).
+ *   values : device float32 [N,H,W]: logits (AAU_IN_LOGITS; sigmoid is evaluated in fp32 on the device exactly as
+ *            1/(1+exp(-x))) or probabilities (AAU_IN_PROB, compared as they are);
+ *   prob_thr: threshold on the probability (0.05 in the reference)
+ *   areas  : device int32 [N] (overwritten);  best : device int32 [2] = {first arg-max index, its area}
+ *   mask   : optional device uint8 [N,H,W] receiving the {0,1} volume, or NULL
+ * Asynchronous on `stream`. */
+int aau_frame_scores(aau_handle* h, const float* values, int input_kind, int N, int H, int W, float prob_thr,
+                     int32_t* areas, int32_t* best, uint8_t* mask, void* stream);
+
+/* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
+ * the device. */
+int aau_device_fault(aau_handle* h);
+
+/* Debug / measurement aids. */
+int aau_num_launches(const aau_handle* h);          /* kernels launched by the last aau_forward */
+/* Copy one named intermediate of the LAST forward (NHWC, activation dtype) to `dst` (device, element count
+ * returned through numel/C); names: x1 x2 x3 x4 p4 bridge d4 d3 d2 (used by layer-by-layer parity tests). */
+int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff);
+/* Force the A-operand staging mode of the 3x3 convolutions: -1 auto, 0 per-tap boxes, 1 halo slabs. */
+int aau_set_option(aau_handle* h, const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAU_H_ */
