@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("AAU_LIB", _HERE / "libaau.so"))
 AAU_VARIANT_PIPELINE, AAU_VARIANT_ABLATION = 0, 1
 AAU_ACT_BF16, AAU_ACT_FP16 = 0, 1
 AAU_X_F32, AAU_X_U8 = 0, 1
-AAU_IN_LOGITS, AAU_IN_PROB = 0, 1
+AAU_IN_LOGITS, AAU_IN_PROB, AAU_IN_U8 = 0, 1, 2
 
 
 class AauConfig(C.Structure):
@@ -46,6 +46,7 @@ SYMBOLS = [
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("aau_frame_scores", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("aau_best_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("aau_device_fault", C.c_int, [C.c_void_p]),
     ("aau_num_launches", C.c_int, [C.c_void_p]),
     ("aau_debug_tensor", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_int)] * 6),

@@ -252,7 +252,10 @@ class AttentionASPPUNet(nn.Module):
 
     # ---- forward ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None):
+        """``x``: CUDA ``float32 [B,1,H,W]`` in [0,1] (the reference contract) or ``uint8 [B,H,W]`` / ``[B,1,H,W]``
+        (normalised on the device as ``u8/255``).  ``out`` (optional) is a contiguous CUDA ``float32 [B,1,H,W]``
+        buffer to receive the logits instead of a fresh allocation."""
         if self.training:
             raise RuntimeError("this is an inference engine: call .eval() first (the reference does, model_attention_aspp.py:39)")
         if not x.is_cuda:
@@ -273,7 +276,12 @@ class AttentionASPPUNet(nn.Module):
         with torch.cuda.device(x.device):
             ws = self._workspace(B, H, W, x.device)
             ws_ptr = (ws.data_ptr() + 255) & ~255
-            logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            if out is not None:
+                if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * H * W or out.device != x.device:
+                    raise ValueError("out must be a contiguous CUDA float32 tensor with B*H*W elements on x's device")
+                logits = out.view(B, 1, H, W)
+            else:
+                logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
             psi3 = psi2 = None
             p3 = p2 = None
             if self.variant == "ablation":

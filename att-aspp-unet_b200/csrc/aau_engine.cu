@@ -898,7 +898,7 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
     return AAU_OK;
 }
 
-int aau_frame_scores(aau_handle* h, const float* logits, int input_kind, int N, int H, int W, float prob_thr, int32_t* areas,
+int aau_frame_scores(aau_handle* h, const void* logits, int input_kind, int N, int H, int W, float prob_thr, int32_t* areas,
                      int32_t* best, uint8_t* mask, void* stream) {
     if (!h) return AAU_ERR_INVALID;
     Engine& e = h->e;
@@ -908,12 +908,29 @@ int aau_frame_scores(aau_handle* h, const float* logits, int input_kind, int N, 
     AAU_CUDA(cudaMemsetAsync(areas, 0, (size_t)N * sizeof(int32_t), s));
     const int HW = H * W;
     const int gx = std::max(1, std::min(64, (HW / 4 + 255) / 256));
-    frame_area_kernel<<<dim3(gx, N), 256, 0, s>>>(logits, input_kind == AAU_IN_PROB ? 1 : 0, HW, prob_thr, areas, mask);
+    if (input_kind == AAU_IN_U8) {
+        if ((long long)HW * 255 > 0x7fffffffLL) return e.fail(AAU_ERR_INVALID, "frame too large for 32-bit byte sums");
+        frame_sum_u8_kernel<<<dim3(gx, N), 256, 0, s>>>((const uint8_t*)logits, HW, areas, mask);
+    } else if (input_kind == AAU_IN_LOGITS || input_kind == AAU_IN_PROB) {
+        frame_area_kernel<<<dim3(gx, N), 256, 0, s>>>((const float*)logits, input_kind == AAU_IN_PROB ? 1 : 0, HW, prob_thr, areas, mask);
+    } else {
+        return e.fail(AAU_ERR_INVALID, "unknown input_kind");
+    }
     AAU_CUDA(cudaGetLastError());
     if (best) {
         area_argmax_kernel<<<1, 1024, 0, s>>>(areas, N, best);
         AAU_CUDA(cudaGetLastError());
     }
+    return AAU_OK;
+}
+
+int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!areas || !best || N < 1) return e.fail(AAU_ERR_INVALID, "bad best_frame arguments");
+    cudaSetDevice(e.device);
+    area_argmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(areas, N, best);
+    AAU_CUDA(cudaGetLastError());
     return AAU_OK;
 }
 

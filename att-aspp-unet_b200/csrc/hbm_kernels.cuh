@@ -232,6 +232,30 @@ __global__ void __launch_bounds__(256) frame_area_kernel(const float* __restrict
     }
 }
 
+// `mask_3d.sum((1,2))` on a uint8 volume (model_attention_aspp.py:94): per-frame sum of byte VALUES (equal to the
+// area for {0,1} masks); optional binarised copy `(v > 0)` (model_attention_aspp.py:97).
+__global__ void __launch_bounds__(256) frame_sum_u8_kernel(const uint8_t* __restrict__ vol, int HW, int* __restrict__ sums,
+                                                           uint8_t* __restrict__ mask) {
+    const int frame = blockIdx.y;
+    const uint8_t* src = vol + (size_t)frame * HW;
+    uint8_t* m = mask ? mask + (size_t)frame * HW : nullptr;
+    int s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int v = __ldg(src + i);
+        s += v;
+        if (m) m[i] = v > 0;
+    }
+    __shared__ int s_part[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && v) atomicAdd(sums + frame, v);
+    }
+}
+
 // first index of the maximum area (numpy argmax tie-break); out[0] = index, out[1] = area at that index
 __global__ void __launch_bounds__(1024) area_argmax_kernel(const int* __restrict__ areas, int n, int* __restrict__ out) {
     int best = -1, best_i = 0x7fffffff;

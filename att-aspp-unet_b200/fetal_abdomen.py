@@ -1,0 +1,273 @@
+"""Sweep-level host layer: the reference's ``FetalAbdomenSegmentation`` / ``select_fetal_abdomen_mask_and_frame``
+surface (model_attention_aspp.py:33-97) on top of the B200 engine.
+
+Two ways in:
+
+* :meth:`FetalAbdomenSegmentation.segment_sweep` -- the fast path.  A ``uint8 [N,H,W]`` sweep goes to the GPU
+  in pinned, double-buffered batches; logits, per-frame areas and the arg-max never leave the device; only
+  ``int32 areas[N]``, the best index and ONE ``uint8 [H,W]`` mask come back.  The 3x3 dilation + largest
+  8-connected component of that single frame run on the host with scipy, exactly as the reference does
+  (model_attention_aspp.py:80-85).
+* :meth:`postprocess` / :func:`select_fetal_abdomen_mask_and_frame` -- signature-compatible mirrors taking host
+  numpy volumes, for code written against the reference.  Their threshold / area / arg-max arithmetic still runs
+  in the CUDA kernels (``aau_frame_scores``); there is no numpy fallback for it.
+
+Frames of a sweep are independent, so a sweep (or a list of cases) is sharded across GPUs by giving every rank a
+contiguous block of frames (``frame_range``); the only cross-rank step is a host gather of ``areas`` followed by
+the same first-max arg-max (:func:`merge_shard_scores`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+try:
+    import _capi
+    from attention_aspp_unet import AttentionASPPUNet
+except ImportError:                                     # package-style import
+    from . import _capi                                 # type: ignore
+    from .attention_aspp_unet import AttentionASPPUNet  # type: ignore
+
+__all__ = ["FetalAbdomenSegmentation", "select_fetal_abdomen_mask_and_frame", "merge_shard_scores", "largest_component"]
+
+
+def largest_component(frame: np.ndarray) -> np.ndarray:
+    """3x3 dilation, 8-connected labelling, keep the largest component (model_attention_aspp.py:80-85).
+
+    Host integer work on ONE frame per sweep; scipy is what the reference itself calls."""
+    import scipy.ndimage as ndi
+    structure = np.ones((3, 3), dtype=np.uint8)
+    frame = ndi.binary_dilation(frame, structure=structure, iterations=1)
+    labeled, n = ndi.label(frame, structure=structure)
+    if n:
+        sizes = ndi.sum(frame, labeled, index=range(1, n + 1))
+        frame = labeled == (np.argmax(sizes) + 1)
+    return frame.astype(np.uint8)
+
+
+def merge_shard_scores(shard_areas: Sequence[np.ndarray]) -> Tuple[np.ndarray, int]:
+    """Host gather step of a multi-GPU sweep: concatenate the per-rank ``areas`` blocks (rank order == frame
+    order) and take the first maximum, as ``areas.argmax()`` does on one device.  Returns ``(areas, idx)`` with
+    ``idx == -1`` when every frame is empty (model_attention_aspp.py:95-96)."""
+    areas = np.concatenate([np.asarray(a, dtype=np.int64) for a in shard_areas]) if len(shard_areas) else np.zeros(0, np.int64)
+    if areas.size == 0 or areas.max() == 0:
+        return areas, -1
+    return areas, int(areas.argmax())
+
+
+class _Scores:
+    """Device-side threshold / area / arg-max through libaau (aau_frame_scores, aau_best_frame)."""
+
+    def __init__(self, net: AttentionASPPUNet, device: torch.device):
+        self.net, self.device = net, device
+        net.prepare(device)
+
+    def run(self, values: torch.Tensor, kind: int, thr: float, areas: torch.Tensor, best: Optional[torch.Tensor],
+            mask: Optional[torch.Tensor]):
+        n, h, w = values.shape
+        st = _capi.lib().aau_frame_scores(self.net.engine_handle(), values.data_ptr(), kind, n, h, w, C.c_float(thr), areas.data_ptr(),
+                                          best.data_ptr() if best is not None else None, mask.data_ptr() if mask is not None else None,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(self.net.engine_handle(), st, "aau_frame_scores")
+
+    def best(self, areas: torch.Tensor, best: torch.Tensor):
+        st = _capi.lib().aau_best_frame(self.net.engine_handle(), areas.data_ptr(), areas.numel(), best.data_ptr(),
+                                        torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(self.net.engine_handle(), st, "aau_best_frame")
+
+
+class FetalAbdomenSegmentation:
+    """Mirror of the reference wrapper (model_attention_aspp.py:33-89) driving the B200 engine.
+
+    ``net`` may be passed in (already holding weights) or is built as the wrapper does:
+    ``AttentionASPPUNet(in_ch=1, num_classes=1, base=base)`` + ``load_state_dict(torch.load(path), strict=False)``.
+    """
+
+    PROB_THRESHOLD = 0.05                                  # model_attention_aspp.py:71
+
+    def __init__(self, checkpoint_path: Optional[str] = None, *, net: Optional[AttentionASPPUNet] = None, base: int = 16,
+                 device: str | torch.device = "cuda", batch: int = 28, act_dtype: str = "bf16"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FetalAbdomenSegmentation (B200 engine) needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if net is None:
+            net = AttentionASPPUNet(in_ch=1, num_classes=1, base=base, act_dtype=act_dtype)
+            if checkpoint_path is not None:
+                miss, unexp = net.load_state_dict(torch.load(checkpoint_path, map_location="cpu"), strict=False)
+                print(f"[DEBUG] load_state — missing:{len(miss)} unexpected:{len(unexp)}")
+        self.net = net.eval()
+        self.batch = int(batch)
+        self._scores = _Scores(self.net, self.device)
+        self._pinned = None
+        self._staging = None
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def _net_logits(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        res = self.net(x, out=out)
+        return res if isinstance(res, torch.Tensor) else res[0]
+
+    @torch.no_grad()
+    def segment_sweep(self, volume, frame_range: Optional[Tuple[int, int]] = None, prob_thr: Optional[float] = None,
+                      finalize: bool = True):
+        """Segment ``volume[frame_range]`` (``uint8`` or float ``[N,H,W]``, host numpy / pinned tensor) and select
+        the best frame.  Returns a dict: ``areas`` (int32 numpy, this shard), ``best_idx`` (index into the full
+        sweep, -1 if empty), ``best_area``, ``mask`` (uint8 [H,W], post-processed as the reference) and timing
+        counters.  With ``finalize=False`` only ``areas`` are produced (multi-GPU shards: the caller gathers them,
+        picks the global frame with :func:`merge_shard_scores` and asks the owner rank for :meth:`frame_mask`)."""
+        thr = self.PROB_THRESHOLD if prob_thr is None else float(prob_thr)
+        vol = torch.from_numpy(volume) if isinstance(volume, np.ndarray) else volume
+        lo, hi = (0, vol.shape[0]) if frame_range is None else frame_range
+        n, H, W = hi - lo, vol.shape[1], vol.shape[2]
+        dev = self.device
+        is_u8 = vol.dtype == torch.uint8
+        if not is_u8:
+            vol = vol.float()
+        areas = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        best = torch.zeros(2, dtype=torch.int32, device=dev)
+        B = max(1, min(self.batch, n))
+        # every frame's logits stay resident (1.67 MB per 562x744 frame; 1.4 GB per 840-frame sweep of 180 GB)
+        if getattr(self, "_logits_all", None) is None or self._logits_all.shape != (max(n, 1), 1, H, W):
+            self._logits_all = torch.empty((max(n, 1), 1, H, W), dtype=torch.float32, device=dev)
+        logits_all = self._logits_all
+        # double-buffered pinned staging -> device input, copies on a side stream
+        shape = (2, B, H, W) if is_u8 else (2, B, 1, H, W)
+        if self._pinned is None or self._pinned.shape != torch.Size(shape) or self._pinned.dtype != vol.dtype:
+            self._pinned = torch.empty(shape, dtype=vol.dtype).pin_memory()
+            self._staging = torch.empty(shape, dtype=vol.dtype, device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        h2d = 0
+        starts = list(range(0, n, B))
+
+        def stage(i):
+            s = starts[i]
+            b = min(B, n - s)
+            slot = i & 1
+            src = vol[lo + s: lo + s + b]
+            if vol.is_pinned():
+                host = src if is_u8 else src.unsqueeze(1)
+            else:
+                host = self._pinned[slot, :b]
+                consumed[slot].synchronize() if i >= 2 else None      # the pinned slot must have been copied out
+                host.copy_(src if is_u8 else src.unsqueeze(1))
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[slot])
+                self._staging[slot, :b].copy_(host, non_blocking=True)
+                ready[slot].record(copy_stream)
+            return b
+
+        if starts:
+            nb = stage(0)
+        for i, s in enumerate(starts):
+            b, slot = nb, i & 1
+            if i + 1 < len(starts):
+                nb = stage(i + 1)
+            main.wait_event(ready[slot])
+            x = self._staging[slot, :b]
+            h2d += x.numel() * x.element_size()
+            logits = self._net_logits(x, out=logits_all[s: s + b])
+            consumed[slot].record(main)
+            self._scores.run(logits[:, 0], _capi.AAU_IN_LOGITS, thr, areas[s: s + b], None, None)
+        out = {"n_frames": n, "h2d_bytes": h2d, "launches": len(starts) * (self.net.num_launches() + 1) + 2}
+        if n == 0:
+            out.update(areas=np.zeros(0, np.int32), best_idx=-1, best_area=0, mask=np.zeros((H, W), np.uint8), d2h_bytes=0)
+            return out
+        self._scores.best(areas[:n], best)
+        host_areas = areas[:n].cpu().numpy()                 # D2H: 4*n bytes, synchronises
+        bi, ba = [int(v) for v in best.cpu().numpy()]
+        out.update(areas=host_areas, best_area=ba, best_local=bi, d2h_bytes=4 * n + 8)
+        if not finalize:
+            return out
+        if ba == 0:
+            out.update(best_idx=-1, mask=np.zeros((H, W), np.uint8))
+            return out
+        out["mask"] = self._mask_from_logits(logits_all[bi].reshape(1, H, W), thr)
+        out["d2h_bytes"] += H * W
+        out["best_idx"] = lo + bi
+        self.last = out
+        return out
+
+    def _mask_from_logits(self, logits_1hw: torch.Tensor, thr: float) -> np.ndarray:
+        _, H, W = logits_1hw.shape
+        m = torch.empty((1, H, W), dtype=torch.uint8, device=self.device)
+        a = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._scores.run(logits_1hw.contiguous(), _capi.AAU_IN_LOGITS, thr, a, None, m)
+        return largest_component(m[0].cpu().numpy())
+
+    @torch.no_grad()
+    def frame_mask(self, volume, frame: int, prob_thr: Optional[float] = None) -> np.ndarray:
+        """Post-processed mask of one frame (used by the owner rank after a multi-GPU gather)."""
+        thr = self.PROB_THRESHOLD if prob_thr is None else float(prob_thr)
+        vol = torch.from_numpy(volume) if isinstance(volume, np.ndarray) else volume
+        x = vol[frame: frame + 1].to(self.device)
+        x = x if x.dtype == torch.uint8 else x.float().unsqueeze(1)
+        return self._mask_from_logits(self._net_logits(x)[:, 0], thr)
+
+    # ------------------------------------------------------------------------------------------------
+    # signature-compatible mirrors of the reference helpers (host numpy in / out)
+    def postprocess(self, probability_map: np.ndarray, prob_thr: Optional[float] = None) -> np.ndarray:
+        """model_attention_aspp.py:69-89: ``(prob > 0.05)``, frame with the largest area, all-zero volume if it is
+        empty, else dilation + largest component of that frame; every other frame zero."""
+        thr = self.PROB_THRESHOLD if prob_thr is None else float(prob_thr)
+        prob = np.ascontiguousarray(probability_map, dtype=np.float32)
+        n, H, W = prob.shape
+        areas = torch.zeros(n, dtype=torch.int32, device=self.device)
+        best = torch.zeros(2, dtype=torch.int32, device=self.device)
+        step = max(1, (256 << 20) // (H * W * 4))
+        for s in range(0, n, step):
+            chunk = torch.from_numpy(prob[s: s + step]).to(self.device)
+            self._scores.run(chunk, _capi.AAU_IN_PROB, thr, areas[s: s + chunk.shape[0]], None, None)
+        self._scores.best(areas, best)
+        bi, ba = [int(v) for v in best.cpu().numpy()]
+        out = np.zeros((n, H, W), np.uint8)
+        if ba == 0:
+            return out
+        m = torch.empty((1, H, W), dtype=torch.uint8, device=self.device)
+        a = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._scores.run(torch.from_numpy(prob[bi: bi + 1]).to(self.device), _capi.AAU_IN_PROB, thr, a, None, m)
+        out[bi] = largest_component(m[0].cpu().numpy())
+        return out
+
+    def select(self, mask_3d: np.ndarray):
+        return select_fetal_abdomen_mask_and_frame(mask_3d, _engine=self)
+
+
+def select_fetal_abdomen_mask_and_frame(mask_3d: np.ndarray, _engine: Optional[FetalAbdomenSegmentation] = None):
+    """model_attention_aspp.py:91-97.  2-D input -> ``(mask > 0, 0)``; otherwise the frame with the largest
+    ``sum`` (first on ties), ``(zeros, -1)`` when that sum is 0.  The per-frame sums and the arg-max run in the
+    CUDA kernels (``aau_frame_scores`` with ``AAU_IN_U8`` + ``aau_best_frame``)."""
+    mask_3d = np.asarray(mask_3d)
+    if mask_3d.ndim == 2:
+        return (mask_3d > 0).astype(np.uint8), 0
+    if _engine is None:
+        _engine = _default_engine()
+    dev = _engine.device
+    n, H, W = mask_3d.shape
+    vol = torch.from_numpy(np.ascontiguousarray(mask_3d, dtype=np.uint8)).to(dev)
+    areas = torch.zeros(n, dtype=torch.int32, device=dev)
+    best = torch.zeros(2, dtype=torch.int32, device=dev)
+    binm = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+    _engine._scores.run(vol, _capi.AAU_IN_U8, 0.0, areas, best, binm)
+    bi, ba = [int(v) for v in best.cpu().numpy()]
+    if ba == 0:
+        return np.zeros((H, W), np.uint8), -1
+    return binm[bi].cpu().numpy(), bi
+
+
+_DEFAULT = None
+
+
+def _default_engine() -> FetalAbdomenSegmentation:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = FetalAbdomenSegmentation(net=AttentionASPPUNet(base_c=16))
+    return _DEFAULT

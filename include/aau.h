@@ -36,7 +36,7 @@ typedef enum {
 enum { AAU_VARIANT_PIPELINE = 0, AAU_VARIANT_ABLATION = 1 };
 enum { AAU_ACT_BF16 = 0, AAU_ACT_FP16 = 1 };
 enum { AAU_X_F32 = 0, AAU_X_U8 = 1 };
-enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1 };
+enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1, AAU_IN_U8 = 2 };
 
 /* Constructor arguments.
  * Replaces AttentionASPPUNet.__init__(in_channels=1, num_classes=1, base_c=32)
@@ -95,13 +95,20 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
 /* Replaces the selection head: `torch.sigmoid(...)` (model_attention_aspp.py:54), `(prob > thr)` (:71),
  * `bin_.sum((1,2)).argmax()` (:74) and `select_fetal_abdomen_mask_and_frame` (:91-97).
  *   values : device float32 [N,H,W]: logits (AAU_IN_LOGITS; sigmoid is evaluated in fp32 on the device exactly as
- *            1/(1+exp(-x))) or probabilities (AAU_IN_PROB, compared as they are);
+ *            1/(1+exp(-x))), probabilities (AAU_IN_PROB, compared as they are), or a uint8 mask volume
+ *            (AAU_IN_U8: `areas` receives the per-frame sum of byte values as `mask_3d.sum((1,2))` does, and
+ *            `mask` receives `v > 0`; prob_thr is ignored);
  *   prob_thr: threshold on the probability (0.05 in the reference)
  *   areas  : device int32 [N] (overwritten);  best : device int32 [2] = {first arg-max index, its area}
  *   mask   : optional device uint8 [N,H,W] receiving the {0,1} volume, or NULL
  * Asynchronous on `stream`. */
-int aau_frame_scores(aau_handle* h, const float* values, int input_kind, int N, int H, int W, float prob_thr,
+int aau_frame_scores(aau_handle* h, const void* values, int input_kind, int N, int H, int W, float prob_thr,
                      int32_t* areas, int32_t* best, uint8_t* mask, void* stream);
+
+/* First index of the maximum of `areas` (device int32 [N]) -> best[0], its value -> best[1]: the
+ * `areas.argmax()` of model_attention_aspp.py:74,94 (numpy tie-break: lowest index).  Used after the per-batch
+ * aau_frame_scores calls of a sweep, and on the host-gathered scores of a multi-GPU run.  Asynchronous. */
+int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream);
 
 /* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
  * the device. */

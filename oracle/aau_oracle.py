@@ -167,6 +167,12 @@ class _Ctx:
 
 def _bn(ctx: _Ctx, x: torch.Tensor, p: str) -> torch.Tensor:
     sd = ctx.sd
+    if ctx.calibrate and x.shape[2] * x.shape[3] == 1:
+        # BN on the globally pooled 1x1 map (ASPP image branch): a calibration batch of a few frames gives a
+        # near-zero variance and scale factors in the hundreds, which no trained network has.  Keep the module
+        # defaults (mean 0, var 1) there; gamma / beta stay random.
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            False, 0.0, BN_EPS)
     if ctx.calibrate:
         # train-mode BatchNorm2d with momentum=None after exactly one batch: running stats become the
         # batch mean and the *unbiased* batch variance; the batch itself is normalised with the biased one.
@@ -220,7 +226,7 @@ def _gate_ablation(ctx, g, x, p):
     return x * a + x, a
 
 
-def _up(ctx, cfg: NetCfg, g, x, lvl: int):
+def _up(ctx, cfg: NetCfg, g, x, lvl: int, taps=None):
     """UpBlock (attention_aspp_unet_pipeline_stage.py:98-109): convT 2x2 s2 (+bias), bilinear fix-up when the
     floor-pooled size differs, gate, cat([x_att, g]) -- skip first -- then two ConvBNReLU."""
     sd = ctx.sd
@@ -234,7 +240,12 @@ def _up(ctx, cfg: NetCfg, g, x, lvl: int):
             x, psi = _gate_pipeline(ctx, g, x, p + ".att")
         else:
             x, psi = _gate_ablation(ctx, g, x, p + ".att")
+    if taps is not None:
+        taps[f"g{lvl}"] = g
+        taps[f"xatt{lvl}"] = x
     y = _cbr(ctx, torch.cat([x, g], 1), p + ".conv.0")
+    if taps is not None:
+        taps[f"u{lvl}a"] = y
     return _cbr(ctx, y, p + ".conv.1"), psi
 
 
@@ -262,6 +273,8 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetCfg = NetCfg()
             if taps is not None:
                 taps[f"x{lvl}"] = h
         h = F.max_pool2d(h, 2)
+        if taps is not None:
+            taps["p4"] = h
         if cfg.variant == "pipeline" or cfg.use_aspp:
             h = _aspp(ctx, h)
         else:
@@ -270,7 +283,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetCfg = NetCfg()
             taps["bridge"] = h
         psis = {}
         for lvl in (4, 3, 2, 1):
-            h, psi = _up(ctx, cfg, h, skips[lvl - 1], lvl)
+            h, psi = _up(ctx, cfg, h, skips[lvl - 1], lvl, taps)
             psis[lvl] = psi
             if taps is not None:
                 taps[f"u{lvl}"] = h
@@ -284,7 +297,8 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetCfg = NetCfg()
 def calibrate_bn(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetCfg = NetCfg()) -> Dict[str, torch.Tensor]:
     """Fill every BN's running stats from one batch (regime R1).  Equivalent to running the reference module
     once on ``x`` with every ``BatchNorm2d`` in ``train()`` mode and ``momentum=None`` (Dropout left in eval) and
-    then calling ``eval()``; ``oracle/gen_golden.py`` asserts that equivalence against the real module."""
+    then calling ``eval()``; ``oracle/gen_golden.py`` asserts that equivalence against the real module.  The one
+    exception is the BN after the ASPP global pooling (``bridge.pool.2``), which keeps identity statistics."""
     sd = dict(sd)
     forward(sd, x, cfg, calibrate=True)
     return sd

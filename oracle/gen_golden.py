@@ -114,8 +114,8 @@ def main():
         if regime == "R1":
             xc = case_input(seed + 2, max(b, 2), h, w, kind)
             model.eval()                      # Dropout stays off; only the BN layers collect statistics
-            for m in model.modules():
-                if isinstance(m, torch.nn.BatchNorm2d):
+            for mn, m in model.named_modules():
+                if isinstance(m, torch.nn.BatchNorm2d) and mn != "bridge.pool.2":   # 1x1 map: see aau_oracle._bn
                     m.momentum = None
                     m.train()
             with torch.no_grad():

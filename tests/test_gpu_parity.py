@@ -1,0 +1,226 @@
+"""GPU parity tests (-m gpu): the CUDA path through libaau.so against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): logits within 2e-2 absolute of the fp32 reference and >= 99.9 % agreement on
+thresholded masks for the literal "random-init weights" regime (R0); frame index and integer post-processing bit exact
+given identical masks.  Regime R1 (BN-calibrated random weights, SURVEY.md section 7 hard part 1) makes a random
+BN+ReLU network chaotic (a single bf16 rounding of the INPUT already moves the fp32 reference's logits by ~5e-3 mean /
+4e-2 max), so there the bar is stated relative to what 16-bit storage can give: the engine must be at least as close to
+the fp32 reference as stock PyTorch bf16 autocast on the same GPU, and the fp16-storage mode must be ~8x closer still.
+"""
+import numpy as np
+import pytest
+import torch
+
+import aau_oracle as O
+from conftest import GOLDEN, golden_case
+
+pytestmark = pytest.mark.gpu
+
+
+def make_net(cfg, sd, dtype="bf16"):
+    from attention_aspp_unet import AttentionASPPUNet
+    kw = dict(base_c=cfg.base_c, act_dtype=dtype)
+    if cfg.variant == "ablation":
+        kw.update(use_att=cfg.use_att, use_aspp=cfg.use_aspp, att_depth=cfg.att_depth)
+    net = AttentionASPPUNet(**kw)
+    net.load_state_dict(sd, strict=True)
+    return net.eval()
+
+
+def r1_case(cfg, shape, seed=11):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(seed)
+    sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), torch.rand(2, 1, H, W, generator=g), cfg)
+    return sd, torch.rand(B, 1, H, W, generator=g)
+
+
+def agreement(a, b, thr):
+    return ((torch.sigmoid(a) > thr) == (torch.sigmoid(b) > thr)).float().mean().item()
+
+
+def autocast_error(sd, x, cfg, ref):
+    """Error of the stock PyTorch bf16 path (autocast on the GPU) against the fp32 CPU reference."""
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = O.forward(sdc, x.cuda(), cfg)
+    out = (out if cfg.variant == "pipeline" else out[0]).float().cpu()
+    return (out - ref).abs()
+
+
+# ------------------------------------------------------------------------------------------------ regime R0
+@pytest.mark.parametrize("c,shape", [(32, (2, 128, 160)), (16, (8, 224, 224)), (32, (1, 562, 744))])
+def test_r0_literal_bar(c, shape):
+    cfg = O.NetCfg(base_c=c)
+    sd = O.make_state_dict(cfg, 2025, "R0")
+    x = torch.rand(*shape[:1], 1, *shape[1:], generator=torch.Generator().manual_seed(2025))
+    ref = O.forward(sd, x, cfg)
+    net = make_net(cfg, sd)
+    out = net(x.cuda()).cpu()
+    net.check_device()
+    assert (out - ref).abs().max().item() <= 2e-2                     # north_star: logits within 2e-2 (bf16)
+    for thr in (0.05, 0.48, 0.5):
+        assert agreement(out, ref, thr) >= 0.999                     # north_star: >= 99.9 % mask agreement
+
+
+# ------------------------------------------------------------------------------------------------ regime R1
+@pytest.mark.parametrize("c,shape", [(32, (2, 141, 93)), (16, (2, 80, 72)), (48, (1, 64, 80)), (32, (1, 562, 744))])
+def test_r1_as_close_as_library_bf16_and_fp16_much_closer(c, shape):
+    cfg = O.NetCfg(base_c=c)
+    sd, x = r1_case(cfg, shape)
+    ref = O.forward(sd, x, cfg)
+    lib = autocast_error(sd, x, cfg, ref)
+    e16 = {}
+    for dt in ("bf16", "fp16"):
+        net = make_net(cfg, sd, dt)
+        out = net(x.cuda()).cpu()
+        net.check_device()
+        assert torch.isfinite(out).all()
+        e16[dt] = (out - ref).abs()
+        assert agreement(out, ref, 0.05) >= 0.999                    # the reference wrapper's own threshold (:71)
+    print(f"\n[R1 c={c} {shape}] mean|err| engine bf16 {e16['bf16'].mean():.5f} fp16 {e16['fp16'].mean():.5f} "
+          f"torch-autocast bf16 {lib.mean():.5f}; max {e16['bf16'].max():.4f} / {e16['fp16'].max():.4f} / {lib.max():.4f}")
+    assert e16["bf16"].mean() <= 1.25 * lib.mean() + 1e-4
+    assert e16["fp16"].mean() <= 0.25 * e16["bf16"].mean() + 1e-4
+    assert e16["fp16"].mean() <= 0.02 * ref.std()                     # ~1 % of the logit spread
+
+
+def test_golden_fixture_full_frame(manifest):
+    """Committed output of the REAL reference on one 562x744 frame (subsampled) vs the engine."""
+    cfg, sd, x, gold = golden_case("pipe_c32_R1_562x744", manifest)
+    s = manifest["pipe_c32_R1_562x744"]["stride"]
+    out = make_net(cfg, sd, "fp16")(x.cuda()).cpu().numpy()[:, :, ::s, ::s]
+    d = np.abs(out - gold["logits"])
+    print(f"\n[golden 562x744 fp16] max {d.max():.4f} mean {d.mean():.5f}")
+    assert d.mean() < 0.01 and d.max() < 0.1
+
+
+@pytest.mark.parametrize("name", ["abl_full_c16_R1_80x72", "abl_noatt_c16_R1_80x72", "abl_noaspp_c16_R1_80x72",
+                                  "abl_neither_c16_R1_80x72", "abl_depth3_c16_R1_81x73", "pipe_c16_R1_141x93", "pipe_c16_R0_64x80"])
+def test_golden_fixtures_variants(name, manifest):
+    """Every ablation variant (config 4) + the pipeline model against outputs of the real reference modules."""
+    cfg, sd, x, gold = golden_case(name, manifest)
+    net = make_net(cfg, sd, "fp16")
+    out = net(x.cuda())
+    net.check_device()
+    if cfg.variant == "pipeline":
+        logits = out
+    else:
+        logits, (psi3, psi2) = out
+        for got, key in ((psi3, "psi3"), (psi2, "psi2")):
+            want = gold[key]
+            assert tuple(got.shape) == want.shape                      # disabled gates: zeros(1,1,1,1)
+            assert np.abs(got.cpu().numpy() - want).max() < 5e-3       # psi in [0,1]
+    d = np.abs(logits.cpu().numpy() - gold["logits"])
+    assert d.mean() < 5e-3 and d.max() < 5e-2, (name, d.mean(), d.max())
+
+
+def test_layer_by_layer_fp16():
+    cfg = O.NetCfg(base_c=32)
+    sd, x = r1_case(cfg, (1, 141, 93))
+    taps = {}
+    O.forward(sd, x, cfg, taps=taps)
+    net = make_net(cfg, sd, "fp16")
+    net(x.cuda())
+    for eng, orc in (("d1.0", "d1.0"), ("x1", "x1"), ("p4", "p4"), ("bridge", "bridge"), ("g4", "g4"), ("x4", "xatt4"), ("d4", "u4"),
+                     ("x3", "xatt3"), ("d3", "u3"), ("x2", "xatt2"), ("d2", "u2"), ("g1", "g1"), ("u1a", "u1a")):
+        got, want = net.debug_tensor(eng).cpu(), taps[orc]
+        assert got.shape == want.shape
+        rel = (got - want).abs().mean() / want.abs().mean()
+        assert rel < 0.02, (eng, rel.item())
+
+
+# ------------------------------------------------------------------------------------------------ properties at full size
+def test_full_size_invariants():
+    cfg = O.NetCfg(base_c=32)
+    sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), torch.rand(2, 1, 96, 96, generator=torch.Generator().manual_seed(1)), cfg)
+    vol = O.synthetic_sweep(5, 562, 744, seed=4, peak=2)
+    net = make_net(cfg, sd)
+    xu8 = torch.from_numpy(vol).cuda()
+    a = net(xu8)
+    b = net(xu8)
+    assert torch.equal(a, b)                                           # deterministic
+    xf = (torch.from_numpy(vol.astype(np.float32)) / 255.0).unsqueeze(1).cuda()
+    assert torch.equal(net(xf), a)                                     # u8 ingest == float(u8)/255 (model_attention_aspp.py:17)
+    one = torch.cat([net(xu8[i:i + 1]) for i in range(5)])
+    assert torch.equal(one, a)                                         # frames are independent: batch size never changes a pixel
+    perm = torch.tensor([3, 0, 4, 1, 2], device="cuda")
+    assert torch.equal(net(xu8[perm]), a[perm])
+    net.set_option("amode", 0)                                         # per-tap staging vs halo slabs: same math
+    c = net(xu8)
+    net.set_option("amode", -1)
+    assert (c - a).abs().max().item() < 1e-5 * max(1.0, a.abs().max().item()) + 1e-4
+    net.check_device()
+
+
+def test_small_and_ragged_sizes():
+    cfg = O.NetCfg(base_c=16)
+    for shape in ((1, 16, 16), (3, 17, 31), (1, 33, 130), (2, 224, 224)):
+        sd, x = r1_case(cfg, shape, seed=shape[1])
+        ref = O.forward(sd, x, cfg)
+        net = make_net(cfg, sd, "fp16")
+        out = net(x.cuda()).cpu()
+        net.check_device()
+        assert out.shape == ref.shape and (out - ref).abs().mean() < 0.02 * max(ref.std().item(), 0.05), shape
+    from attention_aspp_unet import AttentionASPPUNet
+    with pytest.raises(Exception):
+        AttentionASPPUNet(base_c=16).eval()(torch.zeros(1, 1, 8, 64, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ selection head (integer: bit exact)
+def test_frame_scores_bit_exact():
+    from fetal_abdomen import FetalAbdomenSegmentation, select_fetal_abdomen_mask_and_frame
+    from attention_aspp_unet import AttentionASPPUNet
+    seg = FetalAbdomenSegmentation(net=AttentionASPPUNet(base_c=16))
+    g = np.load(GOLDEN / "selection.npz")
+    for vol in ("random", "blobs", "empty", "ties"):                  # golden outputs of the real reference functions
+        m3 = seg.postprocess(g[vol + "_prob"])
+        assert np.array_equal(m3, g[vol + "_mask3d"])
+        m2, idx = select_fetal_abdomen_mask_and_frame(m3, _engine=seg)
+        assert idx == int(g[vol + "_idx"]) and np.array_equal(m2, g[vol + "_mask2d"])
+    rng = np.random.default_rng(0)
+    for n, h, w in ((7, 37, 53), (3, 562, 744), (1, 16, 16), (840, 20, 24)):
+        logits = torch.from_numpy(rng.normal(0, 3, (n, h, w)).astype(np.float32))
+        prob = torch.sigmoid(logits).numpy()
+        for thr in (0.05, 0.48, 0.5):
+            want = O.frame_areas(prob, thr)
+            areas = torch.zeros(n, dtype=torch.int32, device="cuda")
+            best = torch.zeros(2, dtype=torch.int32, device="cuda")
+            mask = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+            seg._scores.run(logits.cuda(), 0, thr, areas, best, mask)
+            got = areas.cpu().numpy()
+            # device expf vs the CPU's sigmoid may differ by one ulp exactly at the threshold: allow 1e-5 of the pixels
+            assert np.abs(got - want).max() <= max(1, int(1e-5 * h * w)), (n, h, w, thr)
+            assert int(best[0]) == int(got.argmax()) and int(best[1]) == int(got.max())
+            assert np.array_equal(mask.cpu().numpy().sum((1, 2)), got)
+    m2, idx = select_fetal_abdomen_mask_and_frame(np.array([[0, 9], [0, 0]], np.uint8))
+    assert idx == 0 and m2.tolist() == [[0, 1], [0, 0]]
+    big = np.zeros((4, 8, 8), np.uint8)
+    big[1, :2] = 200
+    big[3, :4] = 100                                                   # sums of VALUES, not counts: frame 1 and 3 tie at 3200
+    m2, idx = select_fetal_abdomen_mask_and_frame(big, _engine=seg)
+    assert idx == 1 and m2.sum() == 16
+
+
+def test_sweep_engine_matches_oracle_selection():
+    from fetal_abdomen import FetalAbdomenSegmentation, merge_shard_scores
+    cfg = O.NetCfg(base_c=16)
+    sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), torch.rand(2, 1, 96, 128, generator=torch.Generator().manual_seed(1)), cfg)
+    vol = O.synthetic_sweep(23, 96, 128, seed=6, peak=9)
+    net = make_net(cfg, sd)
+    seg = FetalAbdomenSegmentation(net=net, batch=5)
+    logits = torch.cat([net(torch.from_numpy(vol[i:i + 4]).cuda()) for i in range(0, 23, 4)])[:, 0]
+    prob = torch.sigmoid(logits).cpu().numpy()
+    for thr in (0.5, 0.48):
+        res = seg.segment_sweep(vol, prob_thr=thr)
+        m3 = O.postprocess(prob, thr)
+        m2, idx = O.select_fetal_abdomen_mask_and_frame(m3)
+        assert np.array_equal(res["areas"], O.frame_areas(prob, thr))  # bit exact given identical masks
+        assert res["best_idx"] == idx and np.array_equal(res["mask"], m2)
+    # sharded: two contiguous frame blocks + host gather == single pass
+    a = seg.segment_sweep(vol, frame_range=(0, 12), prob_thr=0.5, finalize=False)["areas"]
+    b = seg.segment_sweep(vol, frame_range=(12, 23), prob_thr=0.5, finalize=False)["areas"]
+    areas, gidx = merge_shard_scores([a, b])
+    assert gidx == idx and np.array_equal(areas, O.frame_areas(prob, 0.5))
+    assert np.array_equal(seg.frame_mask(vol, gidx, 0.5), m2)
+    empty = seg.segment_sweep(np.zeros((3, 96, 128), np.uint8), prob_thr=0.999999)
+    assert empty["best_idx"] == -1 and empty["mask"].sum() == 0
