@@ -307,6 +307,19 @@ class AttentionASPPUNet(nn.Module):
     def num_launches(self) -> int:
         return _capi.lib().aau_num_launches(self._handle) if self._handle is not None else 0
 
+    def op_profile(self):
+        """Per-launch records of the last forward: ``[{layer, kernel, ms, flops, bytes}]`` (``ms`` is -1 unless
+        ``set_option("profile", 1)`` was active).  Synchronises."""
+        L = _capi.lib()
+        rows = []
+        for i in range(self.num_launches()):
+            layer, kern = C.c_char_p(), C.c_char_p()
+            ms, fl, by = C.c_float(), C.c_double(), C.c_double()
+            _capi.check(self._handle, L.aau_op_profile(self._handle, i, C.byref(layer), C.byref(kern), C.byref(ms), C.byref(fl), C.byref(by)),
+                        "aau_op_profile")
+            rows.append({"layer": layer.value.decode(), "kernel": kern.value.decode(), "ms": ms.value, "flops": fl.value, "bytes": by.value})
+        return rows
+
     def set_option(self, name: str, value: int):
         if self._handle is None:
             raise RuntimeError("engine not created yet (run a forward or call .prepare(device))")

@@ -76,11 +76,23 @@ struct FwdArgs {
     cudaStream_t stream;
 };
 
+struct OpInfo {
+    std::string name;     // reference layer the launch implements
+    std::string kernel;   // kernel symbol
+    double flops = 0;     // algorithmic FLOPs (2*MAC, dense tap count) of this launch
+    double bytes = 0;     // algorithmic HBM bytes: activations in + out + weights, each once
+};
+
 struct Plan {
     int B = 0, H = 0, W = 0;
     void* ws = nullptr;
     std::vector<std::function<cudaError_t(const FwdArgs&)>> ops;
+    std::vector<OpInfo> info;
+    std::vector<cudaEvent_t> events;     // profile mode: ops.size()+1 events
     std::map<std::string, View> named;
+    ~Plan() {
+        for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+    }
 };
 
 struct Engine {
@@ -100,6 +112,8 @@ struct Engine {
     int* d_err = nullptr;
     int last_launches = 0;
     int opt_amode = -1;
+    int opt_profile = 0;
+    Plan* last_plan = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 
     int fail(int code, const std::string& msg) {
@@ -271,6 +285,7 @@ static int commit_weights(Engine& e) {
     e.dev_allocs.clear();
     e.gw.clear();
     e.plans.clear();
+    e.last_plan = nullptr;
     e.committed = false;
     Prep P(e);
     const int c = e.cfg.base_c;
@@ -466,7 +481,8 @@ static View sub_view(const View& v, int choff, int C) {
 }
 
 // Builds one persistent-GEMM launch over up to 4 problems sharing input geometry, BN and KC.
-static int add_igemm(Engine& e, Plan& plan, const std::vector<ConvDesc>& descs, int patch_aux /*0 none,1 logits,2 psi3,3 psi2*/) {
+static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::vector<ConvDesc>& descs,
+                     int patch_aux /*0 none,1 logits,2 psi3,3 psi2*/) {
     IgemmParams P;
     memset(&P, 0, sizeof(P));
     const ConvDesc& d0 = descs[0];
@@ -556,6 +572,19 @@ static int add_igemm(Engine& e, Plan& plan, const std::vector<ConvDesc>& descs, 
         q.gate_C = d.out.C; q.gate_plus_x = d.gate_plus_x;
     }
     P.total_tiles = tile_begin;
+    OpInfo oi;
+    oi.name = name;
+    oi.kernel = "igemm_tc_kernel";
+    for (const ConvDesc& d : descs) {
+        const double px = (double)d.in.B * d.in.H * d.in.W;
+        oi.flops += 2.0 * px * d.w->K * d.w->N;
+        oi.bytes += px * d.in.C * 2 + (double)d.w->K * d.w->N * 2;
+        if (d.epi == EPI_STORE) oi.bytes += px * d.w->N * 2;
+        if (d.epi == EPI_CONVT) oi.bytes += px * d.w->N * 2;
+        if (d.epi == EPI_GATE) { oi.bytes += px * d.out.C * 2; oi.flops += 2.0 * px * d.w->N; }
+        if (d.epi == EPI_OUTCONV) { oi.bytes += px * 4; oi.flops += 2.0 * px * d.w->N; }
+    }
+    plan.info.push_back(oi);
     const int grid = std::min(P.total_tiles, e.num_sms);
     const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
     plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
@@ -625,11 +654,16 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         ConvDesc d;
         d.w = &e.gw.at(name);
         d.in = in; d.out = out; d.dil = dil; d.epi = EPI_STORE; d.relu = 1;
-        return add_igemm(e, plan, {d}, 0);
+        return add_igemm(e, plan, name, {d}, 0);
     };
     auto pool = [&](const View& in, const View& out) {
         const long long items = (long long)in.B * (in.H / 2) * (in.W / 2) * (in.C / 8);
         const int grid = ew_grid(e, items, 256);
+        OpInfo oi;
+        oi.name = "maxpool " + std::to_string(in.H) + "x" + std::to_string(in.W);
+        oi.kernel = "maxpool2x2_kernel";
+        oi.bytes = (double)items * 16 * 5;
+        plan.info.push_back(oi);
         plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
             maxpool2x2_kernel<<<grid, 256, 0, a.stream>>>(in.p, in.ld, in.choff, in.B, in.H, in.W, in.C, out.p, f16);
             return cudaGetLastError();
@@ -642,6 +676,12 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         const float* b = e.d_stem_b;
         const int grid = ew_grid(e, (long long)B * H * W, 256);
         const size_t smem = (size_t)10 * c * sizeof(float);
+        OpInfo oi;
+        oi.name = "d1.0";
+        oi.kernel = "stem_conv3x3_kernel";
+        oi.flops = 2.0 * B * H * W * 9 * c;
+        oi.bytes = (double)B * H * W * (4 + 2.0 * c);     // fp32 frame in (1 byte when uint8) + NHWC out
+        plan.info.push_back(oi);
         plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
             stem_conv3x3_kernel<<<grid, 256, smem, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, f16);
             return cudaGetLastError();
@@ -663,6 +703,12 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             const float *pT = e.d_poolT, *pb = e.d_poolb, *jT = e.d_projT, *jb = e.d_projb;
             const int pairs = Cin / 2, lanes = std::max(1, 512 / pairs);
             const size_t smem = ((size_t)lanes * Cin + Cin + oc) * sizeof(float);
+            OpInfo oi;
+            oi.name = "bridge.pool (image-level bias)";
+            oi.kernel = "aspp_pool_bias_kernel";
+            oi.flops = 2.0 * B * ((double)Cin * oc + (double)oc * oc);
+            oi.bytes = (double)B * HW * Cin * 2 + ((double)Cin * oc + (double)oc * oc) * 4;
+            plan.info.push_back(oi);
             plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
                 aspp_pool_bias_kernel<<<in.B, 512, smem, a.stream>>>(in.p, HW, Cin, oc, pT, pb, jT, jb, bias_img, f16);
                 return cudaGetLastError();
@@ -675,7 +721,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             ConvDesc d;
             d.w = &e.gw.at("aspp.0");
             d.in = pl[4]; d.out = sub_view(asppcat, 0, oc); d.epi = EPI_STORE; d.relu = 1;
-            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+            if ((r = add_igemm(e, plan, "bridge.blocks.0", {d}, 0))) return r;
         }
         std::vector<ConvDesc> dil3;
         for (int i = 1; i <= 3; ++i) {
@@ -684,13 +730,13 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             d.in = pl[4]; d.out = sub_view(asppcat, i * oc, oc); d.dil = rates[i]; d.epi = EPI_STORE; d.relu = 1;
             dil3.push_back(d);
         }
-        if ((r = add_igemm(e, plan, dil3, 0))) return r;
+        if ((r = add_igemm(e, plan, "bridge.blocks.1-3", dil3, 0))) return r;
         {
             ConvDesc d;
             d.w = &e.gw.at("aspp.project");
             d.in = asppcat; d.out = bo; d.epi = EPI_STORE; d.relu = 1;
             d.bias_img = bias_img; d.bias_img_stride = oc;
-            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+            if ((r = add_igemm(e, plan, "bridge.project", {d}, 0))) return r;
         }
     } else {
         if ((r = conv("bridge.0", pl[4], bo))) return r;
@@ -705,12 +751,17 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             ConvDesc d;
             d.w = &e.gw.at(p + ".up");
             d.in = gin; d.out = fix ? tmpg[l] : gdst; d.epi = EPI_CONVT; d.relu = 0; d.convt_cout = ch[l];
-            if ((r = add_igemm(e, plan, {d}, 0))) return r;
+            if ((r = add_igemm(e, plan, p + ".up", {d}, 0))) return r;
         }
         if (fix) {
             const View in = tmpg[l];
             const long long items = (long long)B * Hs[l] * Ws[l] * (ch[l] / 8);
             const int grid = ew_grid(e, items, 256);
+            OpInfo oi;
+            oi.name = p + ".up bilinear fix-up";
+            oi.kernel = "resize_bilinear_kernel";
+            oi.bytes = (double)items * 16 * 2;
+            plan.info.push_back(oi);
             plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
                 resize_bilinear_kernel<<<grid, 256, 0, a.stream>>>(in.p, in.H, in.W, in.C, gdst.p, gdst.H, gdst.W, gdst.ld, gdst.choff, in.B, f16);
                 return cudaGetLastError();
@@ -724,7 +775,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             d.epi = EPI_GATE; d.relu = 1;
             d.gate_plus_x = e.pipeline() ? 0 : 1;
             const int patch = e.pipeline() ? 0 : (l == 4 ? 2 : (l == 3 ? 3 : 0));
-            if ((r = add_igemm(e, plan, {d}, patch))) return r;
+            if ((r = add_igemm(e, plan, p + ".att", {d}, patch))) return r;
         }
         if ((r = conv(p + ".conv.0", sub_view(cat[l], 0, 2 * ch[l]), ua[l]))) return r;
         if (l > 1) {
@@ -733,7 +784,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             ConvDesc d;
             d.w = &e.gw.at("u1.conv.1");
             d.in = ua[1]; d.out = ua[1]; d.epi = EPI_OUTCONV; d.relu = 1;
-            if ((r = add_igemm(e, plan, {d}, 1))) return r;
+            if ((r = add_igemm(e, plan, "u1.conv.1+out_conv", {d}, 1))) return r;
         }
     }
     return AAU_OK;
@@ -883,18 +934,29 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
         auto np = std::make_unique<Plan>();
         int r = build_plan(e, *np, B, H, W, workspace, &need);
         if (r) return r;
-        if (e.plans.size() >= 8) e.plans.erase(e.plans.begin());
+        if (e.plans.size() >= 8) {
+            if (e.last_plan == e.plans.front().get()) e.last_plan = nullptr;
+            e.plans.erase(e.plans.begin());
+        }
         e.plans.push_back(std::move(np));
         plan = e.plans.back().get();
     }
     FwdArgs a{x, x_dtype, logits, psi3, psi2, (cudaStream_t)stream};
+    const bool prof = e.opt_profile != 0;
+    if (prof && plan->events.size() != plan->ops.size() + 1) {
+        plan->events.resize(plan->ops.size() + 1);
+        for (auto& ev : plan->events) AAU_CUDA(cudaEventCreate(&ev));
+    }
     int n = 0;
     for (auto& op : plan->ops) {
+        if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
         cudaError_t r = op(a);
         if (r != cudaSuccess) return e.fail(AAU_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(r));
         ++n;
     }
+    if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
     e.last_launches = n;
+    e.last_plan = plan;
     return AAU_OK;
 }
 
@@ -949,6 +1011,26 @@ int aau_device_fault(aau_handle* h) {
 
 int aau_num_launches(const aau_handle* h) { return h ? h->e.last_launches : 0; }
 
+int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel, float* ms, double* flops, double* bytes) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    Plan* p = e.last_plan;
+    if (!p || i < 0 || i >= (int)p->ops.size()) return e.fail(AAU_ERR_INVALID, "no such launch in the last forward");
+    const OpInfo& oi = p->info[i];
+    if (layer) *layer = oi.name.c_str();
+    if (kernel) *kernel = oi.kernel.c_str();
+    if (flops) *flops = oi.flops;
+    if (bytes) *bytes = oi.bytes;
+    if (ms) {
+        *ms = -1.f;
+        if (p->events.size() == p->ops.size() + 1) {
+            AAU_CUDA(cudaEventSynchronize(p->events[i + 1]));
+            AAU_CUDA(cudaEventElapsedTime(ms, p->events[i], p->events[i + 1]));
+        }
+    }
+    return AAU_OK;
+}
+
 int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff) {
     if (!h || !name) return AAU_ERR_INVALID;
     Engine& e = h->e;
@@ -972,6 +1054,11 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     if (std::string(name) == "amode") {
         h->e.opt_amode = value;
         h->e.plans.clear();
+        h->e.last_plan = nullptr;
+        return AAU_OK;
+    }
+    if (std::string(name) == "profile") {
+        h->e.opt_profile = value;
         return AAU_OK;
     }
     return h->e.fail(AAU_ERR_INVALID, std::string("unknown option ") + name);

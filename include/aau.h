@@ -116,10 +116,16 @@ int aau_device_fault(aau_handle* h);
 
 /* Debug / measurement aids. */
 int aau_num_launches(const aau_handle* h);          /* kernels launched by the last aau_forward */
+/* Per-launch record of the LAST aau_forward: i in [0, aau_num_launches).  `layer` = the reference layer the
+ * launch implements, `kernel` = kernel symbol, `flops` / `bytes` = its algorithmic work (2*MAC with dense tap
+ * count; activations in + out + weights once).  `ms` is the CUDA-event time between this launch and the next on
+ * the caller's stream when aau_set_option("profile", 1) was on during that forward, else -1 (synchronises). */
+int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel, float* ms, double* flops, double* bytes);
 /* Copy one named intermediate of the LAST forward (NHWC, activation dtype) to `dst` (device, element count
  * returned through numel/C); names: x1 x2 x3 x4 p4 bridge d4 d3 d2 (used by layer-by-layer parity tests). */
 int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff);
-/* Force the A-operand staging mode of the 3x3 convolutions: -1 auto, 0 per-tap boxes, 1 halo slabs. */
+/* Options: "amode" forces the A-operand staging mode of the 3x3 convolutions (-1 auto, 0 per-tap boxes, 1 halo
+ * slabs); "profile" (0/1) records CUDA events around every launch of the following forwards (aau_op_profile). */
 int aau_set_option(aau_handle* h, const char* name, int value);
 
 #ifdef __cplusplus
