@@ -112,6 +112,8 @@ struct Engine {
     int* d_err = nullptr;
     int last_launches = 0;
     int opt_amode = -1;
+    int opt_resident = 1;
+    int opt_ctas = 0;
     int opt_profile = 0;
     Plan* last_plan = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -330,8 +332,8 @@ static int commit_weights(Engine& e) {
             for (int o = 0; o < oc; ++o) {
                 poolb[o] = (float)tp[o];
                 projb[o] = (float)tj[o];
-                for (int i = 0; i < ic; ++i) poolT[(size_t)i * oc + o] = (float)((double)(*wp)[(size_t)o * ic + i] * sp[o]);
-                for (int j = 0; j < oc; ++j) projT[(size_t)j * oc + o] = (float)((double)(*wj)[(size_t)o * 5 * oc + 4 * oc + j] * sj[o]);
+                for (int i = 0; i < ic; ++i) poolT[(size_t)o * ic + i] = (float)((double)(*wp)[(size_t)o * ic + i] * sp[o]);
+                for (int j = 0; j < oc; ++j) projT[(size_t)o * oc + j] = (float)((double)(*wj)[(size_t)o * 5 * oc + 4 * oc + j] * sj[o]);
             }
             if (upload(e, poolT, &e.d_poolT) != cudaSuccess || upload(e, poolb, &e.d_poolb) != cudaSuccess ||
                 upload(e, projT, &e.d_projT) != cudaSuccess || upload(e, projb, &e.d_projb) != cudaSuccess)
@@ -513,24 +515,47 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     }
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
-    P.b_sub_bytes = BN * swz;
-    if (slab) {
-        P.G = 3;
-        P.a_stage_bytes = ((P.TH + 2) * P.TW * swz + 1023) & ~1023;
-        P.stage_bytes = P.a_stage_bytes + 3 * P.b_sub_bytes;
-    } else {
-        const int sub_bytes = 128 * swz + P.b_sub_bytes;
-        const int sub_total = d0.w->taps * (Cin / P.KC);
-        P.G = std::max(1, std::min(std::min(4, sub_total), 40960 / sub_bytes));
-        P.a_stage_bytes = P.G * 128 * swz;
-        P.stage_bytes = P.G * sub_bytes;
-    }
-    P.stage_bytes = (P.stage_bytes + 1023) & ~1023;
-    const int smem_budget = 227 * 1024 - 2048;
-    P.nstages = std::min((int)IGEMM_MAX_STAGES, smem_budget / P.stage_bytes);
-    if (P.nstages < 2) return e.fail(AAU_ERR_INVALID, "pipeline stage does not fit in shared memory");
+    const int nchunk = Cin / P.KC;
+    const int steps = d0.w->taps * nchunk;                        // k-steps (one B sub-block each) per tile
+    P.b_slot_bytes = BN * swz;
+    P.a_slot_bytes = slab ? (((P.TH + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
+    // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
+    const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE;
+    const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : BN);
+    P.CB = cdiv % 64 == 0 ? 64 : (cdiv % 32 == 0 ? 32 : 16);
+    if (d0.epi != EPI_GATE && BN % P.CB) P.CB = 16;
+    P.c_slot_bytes = 128 * P.CB * 2;
+    const int c_bytes = tma_out ? 2 * P.c_slot_bytes : 0;
     P.tmem_cols = 32;
     while (P.tmem_cols < 2 * BN) P.tmem_cols <<= 1;
+    // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the
+    // tensor pipe, so several CTAs share an SM there (TMEM: 512 columns per SM, registers: 3 x 192 threads fit).
+    const bool can_res = descs.size() == 1 && Ntot == BN && e.opt_resident != 0;
+    const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
+    int ctas = BN <= 128 ? 2 : 1;                                 // measured: 2 CTAs co-reside, a third only queues
+    ctas = std::min(ctas, 512 / P.tmem_cols);
+    if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / P.tmem_cols);   // negative: force, skip the occupancy clamp
+    bool ok = false;
+    for (; ctas >= 1 && !ok; --ctas) {
+        const int budget = std::min(233472 / ctas - 6144, 232448 - 4096) - 1024;   // static smem + 1 KB driver reserve + alignment slack
+        for (int pass = 0; pass < 2 && !ok; ++pass) {
+            const bool res = pass == 0 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
+            if (pass == 0 && !res) continue;
+            const int fixed = c_bytes + (res ? res_bytes : 0);
+            const int unit = res ? P.a_slot_bytes : (slab ? P.a_slot_bytes + 3 * P.b_slot_bytes : P.a_slot_bytes + P.b_slot_bytes);
+            const int n = (budget - fixed) / unit;
+            const int need = 2;
+            if (n < need) continue;
+            P.b_resident = res ? 1 : 0;
+            P.nA = std::min((int)IGEMM_MAX_SLOTS, n);
+            P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, n * (slab ? 3 : 1));
+            ok = true;
+        }
+        if (ok) break;
+    }
+    if (!ok) return e.fail(AAU_ERR_INVALID, "pipeline does not fit in shared memory");
+    const int b_region = ((P.nB * P.b_slot_bytes) + 1023) & ~1023;
+    P.b_region_bytes = b_region;
     P.is_fp16 = e.is_fp16() ? 1 : 0;
     P.err = e.d_err;
     P.nprob = (int)descs.size();
@@ -572,6 +597,28 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         q.gate_C = d.out.C; q.gate_plus_x = d.gate_plus_x;
     }
     P.total_tiles = tile_begin;
+    if (tma_out) {
+        const uint32_t cbox[4] = {(uint32_t)P.CB, (uint32_t)P.TW, (uint32_t)P.TH, 1u};
+        if (d0.epi == EPI_STORE || d0.epi == EPI_GATE) {
+            for (int i = 0; i < P.nprob; ++i) {
+                const View& o = descs[i].out;                     // GATE: the skip view that is scaled in place
+                const uint64_t cdims[4] = {(uint64_t)(d0.epi == EPI_GATE ? o.C : Ntot), (uint64_t)o.W, (uint64_t)o.H, (uint64_t)o.B};
+                const uint64_t cstr[3] = {(uint64_t)o.ld * 2, (uint64_t)o.W * o.ld * 2, (uint64_t)o.H * o.W * o.ld * 2};
+                if (!encode_map(e, &P.tmC[i], o.p + (size_t)o.choff * 2, 4, cdims, cstr, cbox, P.CB * 2))
+                    return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output tensor");
+            }
+        } else {
+            // ConvTranspose2d(2,2): view (a,b) of the output holds the pixels (2y+a, 2x+b)
+            const View& o = d0.out;
+            for (int ab = 0; ab < 4; ++ab) {
+                const int a = ab >> 1, b = ab & 1;
+                const uint64_t cdims[4] = {(uint64_t)d0.convt_cout, (uint64_t)((o.W - b + 1) / 2), (uint64_t)((o.H - a + 1) / 2), (uint64_t)o.B};
+                const uint64_t cstr[3] = {(uint64_t)2 * o.ld * 2, (uint64_t)2 * o.W * o.ld * 2, (uint64_t)o.H * o.W * o.ld * 2};
+                if (!encode_map(e, &P.tmC[ab], o.p + ((size_t)(a * o.W + b) * o.ld + o.choff) * 2, 4, cdims, cstr, cbox, P.CB * 2))
+                    return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a transposed-conv output view");
+            }
+        }
+    }
     OpInfo oi;
     oi.name = name;
     oi.kernel = "igemm_tc_kernel";
@@ -585,8 +632,15 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         if (d.epi == EPI_OUTCONV) { oi.bytes += px * 4; oi.flops += 2.0 * px * d.w->N; }
     }
     plan.info.push_back(oi);
-    const int grid = std::min(P.total_tiles, e.num_sms);
-    const size_t smem = (size_t)P.nstages * P.stage_bytes + 1024;
+    const size_t smem = (size_t)P.nA * P.a_slot_bytes + b_region + c_bytes + 1024;
+    // NOTE: cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for this kernel at every shared-memory size
+    // (it does not model TMEM), while two CTAs measurably co-reside (profiles/r01_ctas_experiment.md); if they did
+    // not, the second half of the grid would simply run as a second wave over the same static tile striding.
+    const int grid = std::min(P.total_tiles, e.num_sms * ctas);
+    oi.name += " [" + std::string(slab ? "slab" : "tap") + (P.b_resident ? ",Bres" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+               std::to_string(ctas) + "]";
+    plan.info.back().name = oi.name;
     plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
         IgemmParams Q = P;
         if (patch_aux == 1) Q.prob[0].aux = a.logits;
@@ -624,9 +678,11 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
     const int oc = 16 * c;
     View asppcat, bo = make_view(bump, B, Hs[5], Ws[5], oc);
     float* bias_img = nullptr;
+    float* gap_partial = nullptr;
     if (e.has_aspp()) {
         asppcat = make_view(bump, B, Hs[5], Ws[5], 4 * oc);
         bias_img = (float*)bump.take((size_t)B * oc * sizeof(float));
+        gap_partial = (float*)bump.take((size_t)B * 16 * 8 * c * sizeof(float));
     }
     *need_bytes = bump.off + 1024;
     if (dry) return AAU_OK;
@@ -674,7 +730,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         const View o = ta[1];
         const float* w = e.d_stem_w;
         const float* b = e.d_stem_b;
-        const int grid = ew_grid(e, (long long)B * H * W, 256);
+        const int grid = ew_grid(e, (long long)B * H * ((W + 1) / 2), 256);
         const size_t smem = (size_t)10 * c * sizeof(float);
         OpInfo oi;
         oi.name = "d1.0";
@@ -701,16 +757,27 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             const View in = pl[4];
             const int HW = in.H * in.W, Cin = in.C;
             const float *pT = e.d_poolT, *pb = e.d_poolb, *jT = e.d_projT, *jb = e.d_projb;
-            const int pairs = Cin / 2, lanes = std::max(1, 512 / pairs);
-            const size_t smem = ((size_t)lanes * Cin + Cin + oc) * sizeof(float);
+            const int pairs = Cin / 2, lanes = std::max(1, 256 / pairs);
+            const int splits = 16;
+            float* partial = gap_partial;
+            const size_t smem1 = (size_t)lanes * Cin * sizeof(float);
+            const size_t smem2 = ((size_t)Cin + oc) * sizeof(float);
             OpInfo oi;
-            oi.name = "bridge.pool (image-level bias)";
-            oi.kernel = "aspp_pool_bias_kernel";
-            oi.flops = 2.0 * B * ((double)Cin * oc + (double)oc * oc);
-            oi.bytes = (double)B * HW * Cin * 2 + ((double)Cin * oc + (double)oc * oc) * 4;
+            oi.name = "bridge.pool: global average (partial sums)";
+            oi.kernel = "gap_partial_kernel";
+            oi.bytes = (double)B * HW * Cin * 2;
             plan.info.push_back(oi);
             plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
-                aspp_pool_bias_kernel<<<in.B, 512, smem, a.stream>>>(in.p, HW, Cin, oc, pT, pb, jT, jb, bias_img, f16);
+                gap_partial_kernel<<<dim3(splits, in.B), 256, smem1, a.stream>>>(in.p, HW, Cin, splits, partial, f16);
+                return cudaGetLastError();
+            });
+            oi.name = "bridge.pool: 1x1 conv + project slice -> per-image bias";
+            oi.kernel = "aspp_pool_bias_kernel";
+            oi.flops = 2.0 * B * ((double)Cin * oc + (double)oc * oc);
+            oi.bytes = ((double)Cin * oc + (double)oc * oc) * 4;
+            plan.info.push_back(oi);
+            plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+                aspp_pool_bias_kernel<<<dim3(in.B, 4), 512, smem2, a.stream>>>(partial, splits, HW, Cin, oc, pT, pb, jT, jb, bias_img);
                 return cudaGetLastError();
             });
         }
@@ -841,7 +908,8 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         delete h;
         return AAU_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096) != cudaSuccess ||
+        cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;
@@ -1053,6 +1121,12 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     if (!h || !name) return AAU_ERR_INVALID;
     if (std::string(name) == "amode") {
         h->e.opt_amode = value;
+        h->e.plans.clear();
+        h->e.last_plan = nullptr;
+        return AAU_OK;
+    }
+    if (std::string(name) == "resident" || std::string(name) == "ctas") {
+        (std::string(name) == "resident" ? h->e.opt_resident : h->e.opt_ctas) = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

@@ -13,45 +13,61 @@ namespace aau {
 //  model_attention_aspp.py:17.)  K = 9 is far too small for the tensor cores: one thread per pixel, fp32 FMAs,
 // weights broadcast from shared memory, the C output channels of a pixel written as 16-byte vectors.
 // x_dtype: 0 = float32 [B,1,H,W] (already in [0,1]), 1 = uint8 [B,H,W] (normalised here as float(u8)/255.0f).
+__device__ __forceinline__ float load_px(const void* __restrict__ x, int x_dtype, long long idx) {
+    return x_dtype == 0 ? __ldg((const float*)x + idx) : (float)__ldg((const uint8_t*)x + idx) / 255.0f;
+}
+// Two horizontally adjacent pixels per thread: the 9x4 weights of a 4-channel group are read from shared memory
+// as nine broadcast 16-byte loads and used for 72 FMAs, and the thread writes 2*C*2 contiguous bytes.
 __global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restrict__ x, int x_dtype, int B, int H, int W,
                                                            const float* __restrict__ w9c,   // [9][C], BN scale folded in
                                                            const float* __restrict__ bias,  // [C]
                                                            uint8_t* __restrict__ out, int out_ld, int out_choff, int C, int is_fp16) {
-    extern __shared__ float s_w[];      // [9][C] weights then [C] bias
+    extern __shared__ __align__(16) float s_w[];      // [9][C] weights then [C] bias
     for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) s_w[i] = i < 9 * C ? w9c[i] : bias[i - 9 * C];
     __syncthreads();
-    const long long npix = (long long)B * H * W;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-        const int xw = (int)(p % W);
-        const long long t = p / W;
+    const int Wp = (W + 1) >> 1;                                  // pixel pairs per row
+    const long long npair = (long long)B * H * Wp;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npair; p += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(p % Wp);
+        const long long t = p / Wp;
         const int y = (int)(t % H);
         const long long b = t / H;
-        float v[9];
+        const int x0 = xp * 2;
+        const bool two = x0 + 1 < W;
+        float v[3][4];                                            // rows y-1..y+1, columns x0-1..x0+2
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yy = y + ky - 1, xx = xw + kx - 1;
-                float val = 0.f;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                    const long long idx = (b * H + yy) * W + xx;
-                    val = x_dtype == 0 ? __ldg((const float*)x + idx) : (float)__ldg((const uint8_t*)x + idx) / 255.0f;
-                }
-                v[ky * 3 + kx] = val;
+            for (int kx = 0; kx < 4; ++kx) {
+                const int yy = y + ky - 1, xx = x0 + kx - 1;
+                v[ky][kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? load_px(x, x_dtype, (b * H + yy) * W + xx) : 0.f;
             }
-        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)p * out_ld + out_choff) * 2);
+        uint8_t* dst0 = out + ((((size_t)b * H + y) * W + x0) * out_ld + out_choff) * 2;
+        uint8_t* dst1 = dst0 + (size_t)out_ld * 2;
         for (int c0 = 0; c0 < C; c0 += 8) {
-            float acc[8];
+            float a0[8], a1[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = s_w[9 * C + c0 + i];
+            for (int i = 0; i < 8; ++i) a0[i] = a1[i] = s_w[9 * C + c0 + i];
 #pragma unroll
-            for (int tpi = 0; tpi < 9; ++tpi)
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[tpi], s_w[tpi * C + c0 + i], acc[i]);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wa = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c0);
+                    const float4 wb = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c0 + 4);
+                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-            dst[c0 >> 3] = make_uint4(pack2(acc[0], acc[1], is_fp16), pack2(acc[2], acc[3], is_fp16),
-                                      pack2(acc[4], acc[5], is_fp16), pack2(acc[6], acc[7], is_fp16));
+                    for (int i = 0; i < 8; ++i) {
+                        a0[i] = fmaf(v[ky][kx], w[i], a0[i]);
+                        a1[i] = fmaf(v[ky][kx + 1], w[i], a1[i]);
+                    }
+                }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a0[i] = fmaxf(a0[i], 0.f); a1[i] = fmaxf(a1[i], 0.f); }
+            *reinterpret_cast<uint4*>(dst0 + c0 * 2) = make_uint4(pack2(a0[0], a0[1], is_fp16), pack2(a0[2], a0[3], is_fp16),
+                                                                  pack2(a0[4], a0[5], is_fp16), pack2(a0[6], a0[7], is_fp16));
+            if (two)
+                *reinterpret_cast<uint4*>(dst1 + c0 * 2) = make_uint4(pack2(a1[0], a1[1], is_fp16), pack2(a1[2], a1[3], is_fp16),
+                                                                      pack2(a1[4], a1[5], is_fp16), pack2(a1[6], a1[7], is_fp16));
         }
     }
 }
@@ -93,24 +109,22 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const uint8_t* __restri
 // ASPP image-pooling branch folded into a per-image bias of the project conv (SURVEY.md identity i2;
 // attention_aspp_unet_pipeline_stage.py:75-77,80-83): bilinear up-sampling of a 1x1 map is a broadcast, so
 //   bias_img[b][o] = sum_j Wproj[o][4*Co + j] * relu(sum_i Wpool[j][i] * mean_hw(x[b,:,:,i]) + bpool[j]) + bproj[o].
-// One block per frame.  Phase 1 reduces the frame's pixels per channel with coalesced 4-byte (2-channel) loads
-// and a shared-memory tree across pixel lanes; phases 2/3 are two small mat-vecs on transposed fp32 weights so
-// that consecutive threads read consecutive addresses.
-__global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const uint8_t* __restrict__ x, int HW, int Cin, int Cout,
-                                                             const float* __restrict__ wpoolT,   // [Cin][Cout], BN folded
-                                                             const float* __restrict__ bpool,    // [Cout]
-                                                             const float* __restrict__ wprojT,   // [Cout][Cout] pool slice of project, BN folded
-                                                             const float* __restrict__ bproj,    // [Cout]
-                                                             float* __restrict__ bias_img, int is_fp16) {
-    extern __shared__ float s_buf[];                 // [lanes][Cin] partial sums, then mean[Cin] | v[Cout]
-    const int b = blockIdx.x;
+// Kernel 1 (grid = splits x frames): per-channel partial sums over a slice of the frame's pixels, coalesced
+// 4-byte (2-channel) loads, fixed summation order (no atomics -> deterministic).
+// Kernel 2 finishes the mean and runs the two small mat-vecs (fp32 weights).
+__global__ void __launch_bounds__(256) gap_partial_kernel(const uint8_t* __restrict__ x, int HW, int Cin, int splits,
+                                                          float* __restrict__ partial /* [B][splits][Cin] */, int is_fp16) {
+    extern __shared__ float s_buf[];                 // [lanes][Cin]
+    const int b = blockIdx.y, sp = blockIdx.x;
     const int pairs = Cin >> 1;
-    const int lanes = blockDim.x / pairs;            // pixel lanes
+    const int lanes = blockDim.x / pairs;
     const int pl = threadIdx.x / pairs, cp = threadIdx.x % pairs;
-    float s0 = 0.f, s1 = 0.f;
+    const int per = (HW + splits - 1) / splits;
+    const int p0 = sp * per, p1 = min(HW, p0 + per);
     if (pl < lanes) {
+        float s0 = 0.f, s1 = 0.f;
         const uint32_t* base = reinterpret_cast<const uint32_t*>(x + (size_t)b * HW * Cin * 2) + cp;
-        for (int p = pl; p < HW; p += lanes) {
+        for (int p = p0 + pl; p < p1; p += lanes) {
             const float2 f = unpack2(__ldg(base + (size_t)p * pairs), is_fp16);
             s0 += f.x;
             s1 += f.y;
@@ -119,24 +133,51 @@ __global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const uint8_t* __re
         s_buf[pl * Cin + 2 * cp + 1] = s1;
     }
     __syncthreads();
-    float* mean = s_buf + lanes * Cin;
-    float* v = mean + Cin;
     for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
         float s = 0.f;
         for (int l = 0; l < lanes; ++l) s += s_buf[l * Cin + c];
+        partial[((size_t)b * splits + sp) * Cin + c] = s;
+    }
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// grid = (frames, output slices).  Every block recomputes the (cheap) pooled 1x1 conv `v`, then produces its slice
+// of the per-image bias.  One warp per output channel, lanes split the reduction (coalesced weight rows).
+__global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const float* __restrict__ partial, int splits, int HW, int Cin, int Cout,
+                                                             const float* __restrict__ wpool,    // [Cout][Cin], BN folded
+                                                             const float* __restrict__ bpool,    // [Cout]
+                                                             const float* __restrict__ wproj,    // [Cout][Cout] pool slice of project, BN folded
+                                                             const float* __restrict__ bproj,    // [Cout]
+                                                             float* __restrict__ bias_img) {
+    extern __shared__ float s_buf[];                 // mean[Cin] | v[Cout]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    float* mean = s_buf;
+    float* v = mean + Cin;
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += partial[((size_t)b * splits + sp) * Cin + c];
         mean[c] = s / (float)HW;
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < Cout; o += blockDim.x) {
-        float s = bpool[o];
-        for (int i = 0; i < Cin; ++i) s = fmaf(wpoolT[(size_t)i * Cout + o], mean[i], s);
-        v[o] = fmaxf(s, 0.f);
+    for (int o = warp; o < Cout; o += nwarp) {
+        float s = 0.f;
+        for (int i = lane; i < Cin; i += 32) s = fmaf(__ldg(wpool + (size_t)o * Cin + i), mean[i], s);
+        s = warp_sum_f(s);
+        if (lane == 0) v[o] = fmaxf(s + bpool[o], 0.f);
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < Cout; o += blockDim.x) {
-        float s = bproj[o];
-        for (int j = 0; j < Cout; ++j) s = fmaf(wprojT[(size_t)j * Cout + o], v[j], s);
-        bias_img[(size_t)b * Cout + o] = s;
+    const int per = (Cout + gridDim.y - 1) / gridDim.y;
+    const int o0 = blockIdx.y * per, o1 = min(Cout, o0 + per);
+    for (int o = o0 + warp; o < o1; o += nwarp) {
+        float s = 0.f;
+        for (int j = lane; j < Cout; j += 32) s = fmaf(__ldg(wproj + (size_t)o * Cout + j), v[j], s);
+        s = warp_sum_f(s);
+        if (lane == 0) bias_img[(size_t)b * Cout + o] = s + bproj[o];
     }
 }
 

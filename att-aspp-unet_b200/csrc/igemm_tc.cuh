@@ -1,28 +1,33 @@
 // Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged in
-// shared memory by TMA).  One persistent kernel serves every GEMM-shaped layer of AttentionASPPUNet:
+// shared memory by TMA, results leaving through swizzled shared memory + TMA stores).  One persistent kernel
+// serves every GEMM-shaped layer of AttentionASPPUNet:
 //
 //   rows    (M) : 128 output pixels = a TH x TW patch of one frame (NHWC activations, TH*TW == 128)
 //   columns (N) : BN output channels (<= 256)
 //   depth   (K) : taps x Cin, walked in sub-blocks of KC channels (KC*2 bytes == the TMA/UMMA swizzle width)
 //
-// A operand, two staging modes:
+// A operand (activations), two staging modes, own ring of `nA` slots:
 //   AMODE_TAP  : one TMA box (KC, TW, TH) per (tap, channel chunk), shifted by the tap offset * dilation; image
 //                borders and dilation overhang come back as zeros from the TMA out-of-bounds fill.  Works for
 //                1x1, 3x3 and dilated 3x3.
 //   AMODE_SLAB : 3x3 / dilation 1 only.  One TMA box (KC, TW, TH+2) per (dx, channel chunk) -- a column-shifted
-//                slab with a one-row halo above and below.  The three vertical taps are then three MMAs whose A
-//                descriptors start TW rows apart inside the same slab (TW % 8 == 0 keeps them on the swizzle
-//                period), so every activation byte is fetched from L2 3.75x instead of 9x.
-// B operand: weights [N][K] (K contiguous), one TMA box (KC, BN) per sub-block.
+//                slab with a one-row halo above and below.  The three vertical taps are then three MMA groups whose
+//                A descriptors start TW rows apart inside the same slab (TW % 8 == 0 keeps them on the swizzle
+//                period), so every activation byte is fetched from L2 3.75x (TH=8) instead of 9x.
+// B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
+//   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).  Two accumulator stages in TMEM let the
-// epilogue of tile i overlap the MMAs of tile i+1.
+// epilogue of tile i overlap the MMAs of tile i+1; small-N layers additionally run 2-3 CTAs per SM, because
+// there the single issuing thread (not the tensor pipe) is the limiter (ncu, profiles/r01_*).
 //
 // Epilogues (fp32 math on the accumulator, single rounding to the 16-bit activation type):
-//   EPI_STORE   : + bias (per channel or per image), optional ReLU, NHWC store at a channel offset / pixel stride
-//                 (this is how ASPP branches and skip tensors land directly inside concatenated buffers)
-//   EPI_CONVT   : ConvTranspose2d(2,2): column n = (a*2+b)*Cout + co is scattered to pixel (2y+a, 2x+b)
+//   EPI_STORE   : + bias (per channel or per image), optional ReLU -> swizzled smem -> TMA store into the NHWC
+//                 destination at a channel offset / pixel stride (this is how ASPP branches and skip tensors land
+//                 directly inside concatenated buffers; ragged tiles are clipped by the TMA unit)
+//   EPI_CONVT   : ConvTranspose2d(2,2): column block (a,b) is TMA-stored through a strided view of the output whose
+//                 pixel (x, y) is output pixel (2x+b, 2y+a)
 //   EPI_GATE    : attention gate: psi = sigmoid(w_psi . relu(acc + bias) + b_psi); the skip tensor row is scaled
 //                 by psi (or 1+psi for the ablation flavour) in place; psi optionally written out
 //   EPI_OUTCONV : last decoder conv fused with out_conv: logit = w_out . relu(acc + bias) + b_out (fp32 out)
@@ -38,14 +43,14 @@ namespace aau {
 
 enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
 enum { AMODE_TAP = 0, AMODE_SLAB = 1 };
-enum { IGEMM_THREADS = 192, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_STAGES = 8 };
+enum { IGEMM_THREADS = 192, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12 };
 enum { ERR_PRODUCER_WAIT = 101, ERR_MMA_WAIT_FULL = 102, ERR_MMA_WAIT_TMEM = 103, ERR_EPI_WAIT = 104 };
 
 struct alignas(64) IgemmProblem {
     CUtensorMap tmA;        // activations, 4-D (C, W, H, B)
     CUtensorMap tmB;        // weights, 2-D (K, N)
     const float* bias;      // [N] or [B][bias_img_stride]
-    void* out;              // STORE / CONVT: NHWC destination; GATE: skip tensor, scaled in place
+    void* out;              // GATE: skip tensor, scaled in place
     const float* vec;       // GATE: w_psi[BN]; OUTCONV: w_out[BN]
     float* aux;             // GATE: psi map (may be null); OUTCONV: logits
     int H, W;               // pixel grid of the GEMM rows
@@ -61,12 +66,15 @@ struct alignas(64) IgemmProblem {
 
 struct alignas(64) IgemmParams {
     IgemmProblem prob[IGEMM_MAX_PROBLEMS];
+    CUtensorMap tmC[4];     // output maps: STORE -> one per problem; CONVT -> one per (a,b) of the single problem
     int nprob, total_tiles;
     int amode;              // AMODE_*
-    int KC, G, nstages;     // channels per sub-block, sub-blocks per stage (TAP), smem ring depth
+    int KC;                 // channels per sub-block (16 / 32 / 64)
     int TW, TH, tw_shift;
-    int BN;
-    int a_stage_bytes, b_sub_bytes, stage_bytes;
+    int BN, CB;             // N tile; channels per TMA store (CB*2 bytes == the store swizzle width)
+    int nA, nB, b_resident; // ring depths; b_resident: nB == number of k-steps and B is loaded once
+    int a_slot_bytes, b_slot_bytes, c_slot_bytes;
+    int b_region_bytes;     // nB * b_slot_bytes rounded up to 1024 (the staging tiles behind it need that alignment)
     int tmem_cols;
     int is_fp16;
     int* err;
@@ -108,28 +116,115 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
     return tc;
 }
 
+// KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
+// field, so stepping K by 32 bytes is "+2" on the low word.
+template <int KK>
+__device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t& accumulate) {
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+        ptx::umma_f16(d_tmem, da, db, idesc, accumulate);
+        accumulate = 1;
+    }
+}
+
+template <int KK>
+__device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a, uint64_t* empty_a,
+                                         uint64_t* full_b, uint64_t* empty_b, uint64_t* b_res_bar, uint64_t* tmem_full_bar,
+                                         uint64_t* tmem_empty_bar, uint32_t tmem_base) {
+    const int swz = P.KC * 2;
+    const uint32_t idesc = ptx::make_idesc_f16(128, P.BN, P.is_fp16 != 0);
+    const uint64_t proto = ptx::make_kmajor_desc(0, swz);
+    const uint32_t desc_hi = (uint32_t)(proto >> 32);
+    const uint32_t lo_flags = (uint32_t)proto;                               // LBO field; start address = 0
+    const uint32_t a_base = lo_flags | ((ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4);
+    const uint32_t b_base = lo_flags | ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4);
+    const uint32_t a_slot16 = (uint32_t)P.a_slot_bytes >> 4, b_slot16 = (uint32_t)P.b_slot_bytes >> 4;
+    const uint32_t a_dy16 = (uint32_t)(P.TW * swz) >> 4;                      // slab: next vertical tap = TW rows further
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool res = P.b_resident != 0;
+    if (res) ptx::mbar_wait(b_res_bar, 0, P.err, ERR_MMA_WAIT_FULL);
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(P, t);
+        const IgemmProblem& q = P.prob[tc.pi];
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
+        uint32_t accumulate = 0;
+        if (P.amode == AMODE_TAP) {
+            const int steps = q.taps * q.nchunk;
+            for (int s = 0; s < steps; ++s) {
+                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                const int bslot = res ? s : ib;
+                if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
+                ptx::tc_fence_after();
+                mma_subblock<KK>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                ptx::umma_commit(&empty_a[ia]);
+                if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                if (!res) {
+                    ptx::umma_commit(&empty_b[ib]);
+                    if (++ib == P.nB) { ib = 0; pb ^= 1; }
+                }
+            }
+        } else {
+            int step = 0;
+            for (int dc = 0; dc < 3 * q.nchunk; ++dc) {                       // (dx, channel chunk)
+                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                const uint32_t a_lo = a_base + ia * a_slot16;
+#pragma unroll
+                for (int dyi = 0; dyi < 3; ++dyi, ++step) {
+                    const int bslot = res ? step : ib;
+                    if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
+                    ptx::tc_fence_after();
+                    mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                    if (!res) {
+                        ptx::umma_commit(&empty_b[ib]);
+                        if (++ib == P.nB) { ib = 0; pb ^= 1; }
+                    }
+                }
+                ptx::umma_commit(&empty_a[ia]);
+                if (++ia == P.nA) { ia = 0; pa ^= 1; }
+            }
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);                                // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[IGEMM_MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[IGEMM_MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar[2];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t full_b[IGEMM_MAX_SLOTS], empty_b[IGEMM_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t b_res_bar, c_load_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[2][256];
+    __shared__ __align__(16) float s_vec[256];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // operand tiles need 1024-byte alignment for the 128-byte swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + (size_t)P.nA * P.a_slot_bytes;
+    uint8_t* smem_c = smem_b + (size_t)P.b_region_bytes;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.nprob; ++i) {
             ptx::prefetch_tmap(&P.prob[i].tmA);
             ptx::prefetch_tmap(&P.prob[i].tmB);
         }
-        for (int s = 0; s < P.nstages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
-        }
+        for (int s = 0; s < P.nA; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
+        if (!P.b_resident)
+            for (int s = 0; s < P.nB; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
+        ptx::mbar_init(&b_res_bar, 1);
+        ptx::mbar_init(&c_load_bar, 1);
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
             ptx::mbar_init(&tmem_empty_bar[a], 4);     // one arrive per epilogue warp
@@ -140,56 +235,72 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
         ptx::tmem_alloc(&tmem_base_smem, (uint32_t)P.tmem_cols);
         ptx::tmem_relinquish();
     }
+    if (threadIdx.x >= 64 && P.prob[0].vec != nullptr)                        // GATE / OUTCONV vector, constant per launch
+        for (int i = threadIdx.x - 64; i < P.BN; i += 128) s_vec[i] = P.prob[0].vec[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int swz_bytes = P.KC * 2;
-    const int kk_per_sub = P.KC >> 4;                  // UMMA K = 16 elements = 32 bytes
-
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int ia = 0, ib = 0;
+            uint32_t pa = 0, pb = 0;
+            const bool res = P.b_resident != 0;
+            if (res) {                                                        // whole weight matrix once per CTA
+                const IgemmProblem& q = P.prob[0];
+                const int cin = q.nchunk * P.KC;
+                const int steps = q.taps * q.nchunk;
+                ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
+                for (int s = 0; s < steps; ++s) {
+                    int kcoord = s * P.KC;                                    // TAP order: (tap, chunk)
+                    if (P.amode == AMODE_SLAB) {                              // SLAB order: (dx, chunk, dy)
+                        const int dyi = s % 3, dc = s / 3;
+                        const int dxi = dc / q.nchunk, ch = dc - dxi * q.nchunk;
+                        kcoord = (dyi * 3 + dxi) * cin + ch * P.KC;
+                    }
+                    ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, 0);
+                }
+            }
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(P, t);
                 const IgemmProblem& q = P.prob[tc.pi];
                 if (P.amode == AMODE_TAP) {
-                    const int sub_total = q.taps * q.nchunk;
-                    for (int s0 = 0; s0 < sub_total; s0 += P.G) {
-                        const int nsub = min(P.G, sub_total - s0);
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, P.err, ERR_PRODUCER_WAIT);
-                        uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
-                        uint8_t* sb = sa + P.a_stage_bytes;
-                        const int a_sub_bytes = 128 * swz_bytes;
-                        ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)(nsub * (a_sub_bytes + P.b_sub_bytes)));
-                        for (int j = 0; j < nsub; ++j) {
-                            const int sub = s0 + j;
-                            const int tap = sub / q.nchunk;
-                            const int ch = sub - tap * q.nchunk;
-                            int dy = 0, dx = 0;
-                            if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
-                            ptx::tma_load_4d(sa + j * a_sub_bytes, &q.tmA, &full_bar[stage], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
-                            ptx::tma_load_2d(sb + j * P.b_sub_bytes, &q.tmB, &full_bar[stage], sub * P.KC, tc.n0);
+                    const int steps = q.taps * q.nchunk;
+                    for (int s = 0; s < steps; ++s) {
+                        const int tap = s / q.nchunk;
+                        const int ch = s - tap * q.nchunk;
+                        int dy = 0, dx = 0;
+                        if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
+                        ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
+                        ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
+                        ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
+                        if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                        if (!res) {
+                            ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
+                            ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                            ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC, tc.n0);
+                            if (++ib == P.nB) { ib = 0; pb ^= 1; }
                         }
-                        if (++stage == P.nstages) { stage = 0; phase ^= 1; }
                     }
                 } else {
                     const int cin = q.nchunk * P.KC;
-                    const int slab_bytes = (P.TH + 2) * P.TW * swz_bytes;
+                    const uint32_t slab_bytes = (uint32_t)((P.TH + 2) * P.TW * P.KC * 2);
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         for (int ch = 0; ch < q.nchunk; ++ch) {
-                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, P.err, ERR_PRODUCER_WAIT);
-                            uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
-                            uint8_t* sb = sa + P.a_stage_bytes;
-                            ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)(slab_bytes + 3 * P.b_sub_bytes));
-                            ptx::tma_load_4d(sa, &q.tmA, &full_bar[stage], ch * P.KC, tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
-                            for (int dyi = 0; dyi < 3; ++dyi)
-                                ptx::tma_load_2d(sb + dyi * P.b_sub_bytes, &q.tmB, &full_bar[stage],
-                                                 (dyi * 3 + dxi) * cin + ch * P.KC, tc.n0);
-                            if (++stage == P.nstages) { stage = 0; phase ^= 1; }
+                            ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
+                            ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
+                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                            if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                            if (!res) {
+                                for (int dyi = 0; dyi < 3; ++dyi) {
+                                    ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
+                                    ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                                    ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], (dyi * 3 + dxi) * cin + ch * P.KC, tc.n0);
+                                    if (++ib == P.nB) { ib = 0; pb ^= 1; }
+                                }
+                            }
                         }
                     }
                 }
@@ -198,151 +309,164 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_f16(128, P.BN, P.is_fp16 != 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(P, t);
-                const IgemmProblem& q = P.prob[tc.pi];
-                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
-                uint32_t accumulate = 0;
-                int nstage_k, nsub_full, sub_total;
-                if (P.amode == AMODE_TAP) {
-                    sub_total = q.taps * q.nchunk;
-                    nstage_k = (sub_total + P.G - 1) / P.G;
-                    nsub_full = P.G;
-                } else {
-                    sub_total = 9 * q.nchunk;
-                    nstage_k = 3 * q.nchunk;
-                    nsub_full = 3;
-                }
-                const int a_step = (P.amode == AMODE_TAP) ? 128 * swz_bytes : P.TW * swz_bytes;
-                for (int s = 0; s < nstage_k; ++s) {
-                    const int nsub = min(nsub_full, sub_total - s * nsub_full);
-                    ptx::mbar_wait(&full_bar[stage], phase, P.err, ERR_MMA_WAIT_FULL);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * P.stage_bytes);
-                    const uint32_t sb = sa + (uint32_t)P.a_stage_bytes;
-                    for (int j = 0; j < nsub; ++j) {
-                        for (int k = 0; k < kk_per_sub; ++k) {
-                            const uint64_t da = ptx::make_kmajor_desc(sa + j * a_step + k * 32, swz_bytes);
-                            const uint64_t db = ptx::make_kmajor_desc(sb + j * P.b_sub_bytes + k * 32, swz_bytes);
-                            ptx::umma_f16(d_tmem, da, db, idesc, accumulate);
-                            accumulate = 1;
-                        }
-                    }
-                    ptx::umma_commit(&empty_bar[stage]);        // frees the smem slot once these MMAs retire
-                    if (++stage == P.nstages) { stage = 0; phase ^= 1; }
-                }
-                ptx::umma_commit(&tmem_full_bar[acc]);          // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
+            if (P.KC == 64)      mma_role<4>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else if (P.KC == 32) mma_role<2>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else                 mma_role<1>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
         }
     } else {
         // =========================== epilogue (warps 2..5) ===========================
         const int quarter = warp & 3;                           // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;                      // 0..127
         const int ty = row >> P.tw_shift;
         const int tx = row & (P.TW - 1);
         const int f16 = P.is_fp16;
+        const int c_pitch = P.CB * 2;                           // bytes per staged row == store swizzle width
+        const uint32_t swz_mask = (uint32_t)(c_pitch >> 4) - 1; // 7 / 3 / 1 for 128 / 64 / 32-byte swizzle
         int acc = 0;
         uint32_t acc_phase = 0;
+        int cslot = 0;
+        uint32_t c_phase = 0;
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(P, t);
             const IgemmProblem& q = P.prob[tc.pi];
             const int y = tc.y0 + ty, x = tc.x0 + tx;
             const bool valid = (y < q.H) && (x < q.W);
+            // stage this tile's bias in shared memory (double-buffered by accumulator parity)
+            {
+                const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
+                float* sb = s_bias[acc];
+                if (q.epi == EPI_CONVT) {
+                    for (int i = etid; i < P.BN; i += 128) sb[i] = __ldg(bsrc + (tc.n0 + i) % q.convt_cout);
+                } else {
+                    for (int i = etid; i < P.BN; i += 128) sb[i] = __ldg(bsrc + tc.n0 + i);
+                }
+            }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
             ptx::tc_fence_after();
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // bias visible to the four epilogue warps
+            const float* sb = s_bias[acc];
             const uint32_t taddr = tmem_base + (uint32_t)(acc * P.BN) + ((uint32_t)(quarter * 32) << 16);
-            const float* bias = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0) + tc.n0;
-            float dot = 0.f;                                    // GATE / OUTCONV reduction over channels
-            uint8_t* out_row = nullptr;
-            if (q.epi == EPI_STORE)
-                out_row = (uint8_t*)q.out + ((((size_t)tc.b * q.outH + y) * q.outW + x) * q.out_ld + q.out_choff + tc.n0) * 2;
 
-            for (int c0 = 0; c0 < P.BN; c0 += 32) {
-                uint32_t r[32];
-                const int ncol = min(32, P.BN - c0);
-                if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0, r);
-                else            ptx::tmem_ld_32x16(taddr + c0, r);
-                ptx::tmem_ld_wait();
-                if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+            if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+                for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
+                    // the TMA store that used this staging slot two groups ago must have finished reading it
+                    if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
+                    for (int cc = 0; cc < P.CB; cc += 32) {
+                        uint32_t r[32];
+                        const int ncol = min(32, P.CB - cc);
+                        if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
+                        else            ptx::tmem_ld_32x16(taddr + c0 + cc, r);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        if (v * 8 < ncol) {
-                            float f[8];
+                        for (int v = 0; v < 4; ++v) {
+                            if (v * 8 < ncol) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8 + 4);
+                                float f[8];
+                                f[0] = __uint_as_float(r[v * 8 + 0]) + b0.x; f[1] = __uint_as_float(r[v * 8 + 1]) + b0.y;
+                                f[2] = __uint_as_float(r[v * 8 + 2]) + b0.z; f[3] = __uint_as_float(r[v * 8 + 3]) + b0.w;
+                                f[4] = __uint_as_float(r[v * 8 + 4]) + b1.x; f[5] = __uint_as_float(r[v * 8 + 5]) + b1.y;
+                                f[6] = __uint_as_float(r[v * 8 + 6]) + b1.z; f[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
+                                if (q.relu) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]);
-                            if (q.epi == EPI_STORE) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    f[i] += __ldg(bias + c0 + v * 8 + i);
-                                    if (q.relu) f[i] = fmaxf(f[i], 0.f);
+                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                                 }
-                                if (valid) {
-                                    uint4 o = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
-                                    *reinterpret_cast<uint4*>(out_row + (c0 + v * 8) * 2) = o;
-                                }
-                            } else {
-                                const int n = tc.n0 + c0 + v * 8;
-                                const int ab = n / q.convt_cout;
-                                const int co = n - ab * q.convt_cout;
-                                const int oy = 2 * y + (ab >> 1), ox = 2 * x + (ab & 1);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] += __ldg(q.bias + co + i);
-                                if (valid && oy < q.outH && ox < q.outW) {
-                                    uint4 o = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
-                                    uint8_t* dst = (uint8_t*)q.out + ((((size_t)tc.b * q.outH + oy) * q.outW + ox) * q.out_ld + q.out_choff + co) * 2;
-                                    *reinterpret_cast<uint4*>(dst) = o;
-                                }
+                                const uint4 o = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
+                                uint32_t off = (uint32_t)(row * c_pitch + (cc + v * 8) * 2);
+                                off ^= ((off >> 7) & swz_mask) << 4;          // TMA swizzle pattern of the staging tile
+                                *reinterpret_cast<uint4*>(cs + off) = o;
                             }
                         }
                     }
-                } else {
-                    // GATE / OUTCONV: dot += sum_n relu(acc_n + bias_n) * vec_n
+                    if (c0 + P.CB >= P.BN) {                                  // accumulator fully read: free the TMEM stage
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (etid == 0) {
+                        const int n = tc.n0 + c0;
+                        const void* tm;
+                        int cch;
+                        if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
+                        else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    cslot ^= 1;
+                }
+            } else {
+                // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel
+                float dot = 0.f;
+                for (int c0 = 0; c0 < P.BN; c0 += 32) {
+                    uint32_t r[32];
+                    const int ncol = min(32, P.BN - c0);
+                    if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0, r);
+                    else            ptx::tmem_ld_32x16(taddr + c0, r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i < ncol) {
-                            float f = __uint_as_float(r[i]) + __ldg(bias + c0 + i);
-                            f = fmaxf(f, 0.f);
-                            dot = fmaf(f, __ldg(q.vec + tc.n0 + c0 + i), dot);
+                    for (int v = 0; v < 8; ++v) {
+                        if (v * 4 < ncol) {
+                            const float4 b = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
+                            const float4 w = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
+                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 0]) + b.x, 0.f), w.x, dot);
+                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 1]) + b.y, 0.f), w.y, dot);
+                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 2]) + b.z, 0.f), w.z, dot);
+                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 3]) + b.w, 0.f), w.w, dot);
                         }
                     }
                 }
-            }
-            // the accumulator has been read into registers: hand the TMEM stage back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
-
-            if (q.epi == EPI_OUTCONV) {
-                if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
-            } else if (q.epi == EPI_GATE) {
-                const float a = 1.f / (1.f + expf(-(dot + q.scalar)));
-                const float scale = q.gate_plus_x ? (1.f + a) : a;
-                if (valid) {
-                    if (q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
-                    uint4* xr = reinterpret_cast<uint4*>((uint8_t*)q.out + ((((size_t)tc.b * q.outH + y) * q.outW + x) * q.out_ld + q.out_choff) * 2);
-                    for (int j = 0; j < (q.gate_C >> 3); ++j) {
-                        uint4 v = xr[j];
-                        float2 p0 = unpack2(v.x, f16), p1 = unpack2(v.y, f16), p2 = unpack2(v.z, f16), p3 = unpack2(v.w, f16);
-                        v.x = pack2(p0.x * scale, p0.y * scale, f16);
-                        v.y = pack2(p1.x * scale, p1.y * scale, f16);
-                        v.z = pack2(p2.x * scale, p2.y * scale, f16);
-                        v.w = pack2(p3.x * scale, p3.y * scale, f16);
-                        xr[j] = v;
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (q.epi == EPI_OUTCONV) {
+                    if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
+                } else {
+                    const float a = 1.f / (1.f + expf(-(dot + q.scalar)));
+                    const float scale = q.gate_plus_x ? (1.f + a) : a;
+                    if (valid && q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
+                    // scale the skip tile in place: TMA load (L2 hit: the same bytes were just streamed in as the A
+                    // operand) -> multiply this thread's pixel row in shared memory -> TMA store, CB channels at a time
+                    for (int c0 = 0; c0 < q.gate_C; c0 += P.CB) {
+                        uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
+                        if (etid == 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            ptx::mbar_expect_tx(&c_load_bar, (uint32_t)P.c_slot_bytes);
+                            ptx::tma_load_4d(cs, &P.tmC[0], &c_load_bar, c0, tc.x0, tc.y0, tc.b);
+                        }
+                        ptx::mbar_wait(&c_load_bar, c_phase, P.err, ERR_EPI_WAIT);
+                        c_phase ^= 1;
+                        for (int v = 0; v < (c_pitch >> 4); ++v) {
+                            uint32_t off = (uint32_t)(row * c_pitch + v * 16);
+                            off ^= ((off >> 7) & swz_mask) << 4;
+                            uint4 val = *reinterpret_cast<uint4*>(cs + off);
+                            const float2 p0 = unpack2(val.x, f16), p1 = unpack2(val.y, f16), p2 = unpack2(val.z, f16), p3 = unpack2(val.w, f16);
+                            val.x = pack2(p0.x * scale, p0.y * scale, f16);
+                            val.y = pack2(p1.x * scale, p1.y * scale, f16);
+                            val.z = pack2(p2.x * scale, p2.y * scale, f16);
+                            val.w = pack2(p3.x * scale, p3.y * scale, f16);
+                            *reinterpret_cast<uint4*>(cs + off) = val;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (etid == 0) {
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        cslot ^= 1;
                     }
                 }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores landed
     }
 
     ptx::tc_fence_before();

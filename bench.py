@@ -173,6 +173,9 @@ def run_engine(args):
     net = AttentionASPPUNet(base_c=BASE_C, act_dtype=args.dtype)
     net.load_state_dict(sd, strict=True)
     net.eval().prepare(dev)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        net.set_option(k, int(v))
     seg = FetalAbdomenSegmentation(net=net, batch=args.batch, device=dev)
     vol_np = make_sweep(seed=2025 + rank)                       # N>1: one case per rank (config[2], sharded by case)
     vol_pinned = torch.from_numpy(vol_np).pin_memory()
@@ -302,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=28)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (amode, resident, ctas)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample of the engine arm")
     args = ap.parse_args()

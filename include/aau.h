@@ -125,7 +125,9 @@ int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel
  * returned through numel/C); names: x1 x2 x3 x4 p4 bridge d4 d3 d2 (used by layer-by-layer parity tests). */
 int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff);
 /* Options: "amode" forces the A-operand staging mode of the 3x3 convolutions (-1 auto, 0 per-tap boxes, 1 halo
- * slabs); "profile" (0/1) records CUDA events around every launch of the following forwards (aau_op_profile). */
+ * slabs); "resident" (1/0) allows / forbids keeping a layer's whole weight matrix in shared memory; "ctas" (0 auto,
+ * 1..3) caps the CTAs per SM of the GEMM kernel; "profile" (0/1) records CUDA events around every launch of the
+ * following forwards (aau_op_profile). */
 int aau_set_option(aau_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -220,6 +220,7 @@ def test_sweep_engine_matches_oracle_selection():
         assert np.array_equal(res["areas"], O.frame_areas(prob, thr))  # bit exact given identical masks
         assert res["best_idx"] == idx and np.array_equal(res["mask"], m2)
     # sharded: two contiguous frame blocks + host gather == single pass
+    m2, idx = O.select_fetal_abdomen_mask_and_frame(O.postprocess(prob, 0.5))
     a = seg.segment_sweep(vol, frame_range=(0, 12), prob_thr=0.5, finalize=False)["areas"]
     b = seg.segment_sweep(vol, frame_range=(12, 23), prob_thr=0.5, finalize=False)["areas"]
     areas, gidx = merge_shard_scores([a, b])
