@@ -42,6 +42,7 @@ struct KeySpec {
 
 struct GemmW {                // packed GEMM operand, device resident
     void* dB = nullptr;       // [N][K] 16-bit, K contiguous
+    void* dBdx = nullptr;     // 3x3 only, N in {16,32,64}: [3N][3Cin], row j*N+o = W[o][:][dy][dx=j] (AMODE_DXN)
     float* dbias = nullptr;   // fp32
     float* dvec = nullptr;    // optional fp32 vector (gate w_psi, out_conv w)
     float scalar = 0.f;       // optional scalar (gate b_psi, out_conv b)
@@ -278,6 +279,20 @@ static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::
                 Bm[(size_t)o * g.K + (size_t)tp * cin + i] = (float)((double)(*w)[((size_t)o * cin + i) * taps + tp] * s[o]);
     }
     int r = finish_gemm(e, g, Bm, bias);
+    if (!r && taps == 9 && (cout == 16 || cout == 32 || cout == 64)) {
+        // horizontal taps stacked along N: Bd[j*cout + o][dy*cin + i] = W[o][i][dy][j] * s[o]
+        std::vector<uint16_t> bd((size_t)3 * cout * 3 * cin);
+        const bool f16 = e.is_fp16();
+        for (int j = 0; j < 3; ++j)
+            for (int o = 0; o < cout; ++o)
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int i = 0; i < cin; ++i)
+                        bd[((size_t)j * cout + o) * 3 * cin + (size_t)dy * cin + i] =
+                            to16((float)((double)(*w)[((size_t)o * cin + i) * 9 + dy * 3 + j] * s[o]), f16);
+        uint16_t* d = nullptr;
+        if (upload(e, bd, &d) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "weight upload failed");
+        g.dBdx = d;
+    }
     e.gw[name] = g;
     return r;
 }
@@ -497,12 +512,24 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     if (!BN) return e.fail(AAU_ERR_INVALID, "output channels must be a multiple of 16");
     if (d0.epi == EPI_GATE || d0.epi == EPI_OUTCONV)
         if (BN != Ntot) return e.fail(AAU_ERR_INVALID, "gate / out_conv epilogues need all channels in one tile");
-    P.BN = BN;
     const bool conv3 = d0.w->taps == 9;
     bool slab = conv3 && d0.dil == 1 && BN <= 128;
     if (e.opt_amode == 0) slab = false;
     if (e.opt_amode == 1 && conv3 && d0.dil == 1 && BN <= 128) slab = true;
-    P.amode = slab ? AMODE_SLAB : AMODE_TAP;
+    bool dxn = conv3 && d0.dil == 1 && descs.size() == 1 && d0.w->dBdx != nullptr && Ntot == BN &&
+               (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 2);
+    if (dxn) {                                                     // does the dx-stacked pipeline fit in shared memory?
+        const int sw = P.KC * 2, a = 6 * 32 * sw, b = 3 * BN * sw, st = 3 * (Cin / P.KC);
+        const int rb = (st * b + 1023) & ~1023, cb = d0.epi == EPI_STORE ? 2 * 128 * BN * 2 : 0, budget1 = 225280;
+        const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * (a + 3 * b) <= budget1);
+        if (!fits) dxn = false;
+    }
+    if (dxn) slab = true;                                          // shares the slab geometry code below
+    P.amode = dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP);
+    const int n_out = BN;
+    if (dxn) BN = 3 * n_out;                                       // MMA N: the three dx taps side by side
+    P.BN = BN;
+    P.n_out = n_out;
     // tile shape: minimise padded pixels (and, for slabs, halo overhead)
     const int H = d0.in.H, W = d0.in.W;
     double best = 1e30;
@@ -513,31 +540,34 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         if (slab) cost *= 1.0 + 0.5 * 2.0 / th;     // halo rows cost bandwidth, not MMA time
         if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
     }
+    P.VW = P.TW;
+    if (dxn) { P.TW = 32; P.TH = 4; P.VW = 30; }
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
     const int nchunk = Cin / P.KC;
-    const int steps = d0.w->taps * nchunk;                        // k-steps (one B sub-block each) per tile
+    const int steps = (dxn ? 3 : d0.w->taps) * nchunk;            // k-steps (one B sub-block each) per tile
     P.b_slot_bytes = BN * swz;
     P.a_slot_bytes = slab ? (((P.TH + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
     // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
     const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE;
-    const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : BN);
+    const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : n_out);
     P.CB = cdiv % 64 == 0 ? 64 : (cdiv % 32 == 0 ? 32 : 16);
-    if (d0.epi != EPI_GATE && BN % P.CB) P.CB = 16;
+    if (d0.epi != EPI_GATE && n_out % P.CB) P.CB = 16;
     P.c_slot_bytes = 128 * P.CB * 2;
     const int c_bytes = tma_out ? 2 * P.c_slot_bytes : 0;
+    P.acc_stages = (BN > 128 && BN <= 256 && dxn) ? 1 : 2;        // dx-stacked N = 192: one stage, two CTAs overlap instead
     P.tmem_cols = 32;
-    while (P.tmem_cols < 2 * BN) P.tmem_cols <<= 1;
+    while (P.tmem_cols < P.acc_stages * BN) P.tmem_cols <<= 1;
     // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the
     // tensor pipe, so several CTAs share an SM there (TMEM: 512 columns per SM, registers: 3 x 192 threads fit).
-    const bool can_res = descs.size() == 1 && Ntot == BN && e.opt_resident != 0;
+    const bool can_res = descs.size() == 1 && Ntot == n_out && e.opt_resident != 0;
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
-    int ctas = BN <= 128 ? 2 : 1;                                 // measured: 2 CTAs co-reside, a third only queues
+    int ctas = (BN <= 128 || P.acc_stages == 1) ? 2 : 1;          // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / P.tmem_cols);
     if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / P.tmem_cols);   // negative: force, skip the occupancy clamp
     bool ok = false;
     for (; ctas >= 1 && !ok; --ctas) {
-        const int budget = std::min(233472 / ctas - 6144, 232448 - 4096) - 1024;   // static smem + 1 KB driver reserve + alignment slack
+        const int budget = std::min(233472 / ctas - 7168, 232448 - 6144) - 1024;   // static smem + 1 KB driver reserve + alignment slack
         for (int pass = 0; pass < 2 && !ok; ++pass) {
             const bool res = pass == 0 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
             if (pass == 0 && !res) continue;
@@ -572,10 +602,10 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH + 2 : P.TH), 1u};
         if (!encode_map(e, &q.tmA, d.in.p + (size_t)d.in.choff * 2, 4, adims, astr, abox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
-        const uint64_t bdims[2] = {(uint64_t)d.w->K, (uint64_t)d.w->N};
-        const uint64_t bstr[1] = {(uint64_t)d.w->K * 2};
+        const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
+        const uint64_t bstr[1] = {bdims[0] * 2};
         const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)BN};
-        if (!encode_map(e, &q.tmB, d.w->dB, 2, bdims, bstr, bbox, swz))
+        if (!encode_map(e, &q.tmB, dxn ? d.w->dBdx : d.w->dB, 2, bdims, bstr, bbox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight tensor");
         q.bias = d.bias_img ? d.bias_img : d.w->dbias;
         q.bias_img_stride = d.bias_img ? d.bias_img_stride : 0;
@@ -584,11 +614,14 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         q.aux = d.aux;
         q.scalar = d.w->scalar;
         q.H = H; q.W = W;
-        q.tiles_x = (W + P.TW - 1) / P.TW;
+        q.tiles_x = (W + P.VW - 1) / P.VW;
         q.tiles_per_img = q.tiles_x * ((H + P.TH - 1) / P.TH);
         q.m_tiles = d.in.B * q.tiles_per_img;
-        q.n_tiles = Ntot / BN;
+        q.n_tiles = Ntot / n_out;
         q.tile_begin = tile_begin;
+        q.fd_n_tiles = make_fastdiv((uint32_t)q.n_tiles);
+        q.fd_tiles_per_img = make_fastdiv((uint32_t)q.tiles_per_img);
+        q.fd_tiles_x = make_fastdiv((uint32_t)q.tiles_x);
         tile_begin += q.m_tiles * q.n_tiles;
         q.taps = d.w->taps; q.dil = d.dil; q.nchunk = Cin / P.KC;
         q.epi = d.epi; q.relu = d.relu;
@@ -598,7 +631,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     }
     P.total_tiles = tile_begin;
     if (tma_out) {
-        const uint32_t cbox[4] = {(uint32_t)P.CB, (uint32_t)P.TW, (uint32_t)P.TH, 1u};
+        const uint32_t cbox[4] = {(uint32_t)P.CB, (uint32_t)P.VW, (uint32_t)P.TH, 1u};
         if (d0.epi == EPI_STORE || d0.epi == EPI_GATE) {
             for (int i = 0; i < P.nprob; ++i) {
                 const View& o = descs[i].out;                     // GATE: the skip view that is scaled in place
@@ -637,7 +670,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // (it does not model TMEM), while two CTAs measurably co-reside (profiles/r01_ctas_experiment.md); if they did
     // not, the second half of the grid would simply run as a second wave over the same static tile striding.
     const int grid = std::min(P.total_tiles, e.num_sms * ctas);
-    oi.name += " [" + std::string(slab ? "slab" : "tap") + (P.b_resident ? ",Bres" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
+    oi.name += " [" + std::string(dxn ? "dxn" : (slab ? "slab" : "tap")) + (P.b_resident ? ",Bres" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
                " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
@@ -908,7 +941,7 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         delete h;
         return AAU_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096) != cudaSuccess ||
+    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144) != cudaSuccess ||
         cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;

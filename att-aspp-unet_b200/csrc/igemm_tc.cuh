@@ -14,11 +14,18 @@
 //                slab with a one-row halo above and below.  The three vertical taps are then three MMA groups whose
 //                A descriptors start TW rows apart inside the same slab (TW % 8 == 0 keeps them on the swizzle
 //                period), so every activation byte is fetched from L2 3.75x (TH=8) instead of 9x.
+//   AMODE_DXN  : 3x3 / dilation 1 / Cout <= 64.  The three horizontal taps are stacked along N instead of being
+//                three shifted A reads: ONE slab (KC, 32, TH+2) per channel chunk, B = [W(dx=-1); W(0); W(+1)]
+//                (3*Cout rows), so an MMA of N' = 3*Cout produces E_dx = A . W_dx for all three dx at once and the
+//                epilogue forms out[x] = E_-1[x-1] + E_0[x] + E_+1[x+1] with two warp shuffles per channel (a warp
+//                is one 32-pixel row of the tile; its 30 inner pixels are valid outputs, tiles overlap by two
+//                columns).  3x fewer MMAs and A loads -- what the small-N layers, which are limited by the
+//                shared-memory read of the A operand (64 cycles per MMA whatever N), need.
 // B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
 //   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).  Two accumulator stages in TMEM let the
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = epilogue (two warps per TMEM lane quarter warp_id % 4, splitting the channel range).  Two accumulator stages in TMEM let the
 // epilogue of tile i overlap the MMAs of tile i+1; small-N layers additionally run 2-3 CTAs per SM, because
 // there the single issuing thread (not the tensor pipe) is the limiter (ncu, profiles/r01_*).
 //
@@ -42,9 +49,24 @@
 namespace aau {
 
 enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
-enum { AMODE_TAP = 0, AMODE_SLAB = 1 };
-enum { IGEMM_THREADS = 192, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12 };
+enum { AMODE_TAP = 0, AMODE_SLAB = 1, AMODE_DXN = 2 };
+enum { IGEMM_THREADS = 320, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12 };
 enum { ERR_PRODUCER_WAIT = 101, ERR_MMA_WAIT_FULL = 102, ERR_MMA_WAIT_TMEM = 103, ERR_EPI_WAIT = 104 };
+
+// Division by a launch-time constant as multiply-high + shift (the tile decode runs once per tile per role and four
+// hardware integer divisions were ~25 % of the epilogue's instructions).  Exact for n < 2^31.
+struct FastDiv {
+    uint32_t mul, shr;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.shr = s;
+    f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(n, f.mul) + n) >> f.shr; }
 
 struct alignas(64) IgemmProblem {
     CUtensorMap tmA;        // activations, 4-D (C, W, H, B)
@@ -55,6 +77,7 @@ struct alignas(64) IgemmProblem {
     float* aux;             // GATE: psi map (may be null); OUTCONV: logits
     int H, W;               // pixel grid of the GEMM rows
     int tiles_x, tiles_per_img, m_tiles, n_tiles, tile_begin;
+    FastDiv fd_n_tiles, fd_tiles_per_img, fd_tiles_x;
     int taps, dil, nchunk;  // taps in {1, 9}; nchunk = Cin / KC
     int epi, relu, bias_img_stride;
     int outH, outW, out_ld, out_choff;
@@ -71,11 +94,14 @@ struct alignas(64) IgemmParams {
     int amode;              // AMODE_*
     int KC;                 // channels per sub-block (16 / 32 / 64)
     int TW, TH, tw_shift;
-    int BN, CB;             // N tile; channels per TMA store (CB*2 bytes == the store swizzle width)
+    int BN, CB;             // MMA N (DXN: 3*Cout); channels per TMA store (CB*2 bytes == the store swizzle width)
+    int n_out;              // output channels per tile (== BN except DXN: BN / 3)
+    int VW;                 // valid output columns per tile (== TW except DXN: TW - 2)
     int nA, nB, b_resident; // ring depths; b_resident: nB == number of k-steps and B is loaded once
     int a_slot_bytes, b_slot_bytes, c_slot_bytes;
     int b_region_bytes;     // nB * b_slot_bytes rounded up to 1024 (the staging tiles behind it need that alignment)
     int tmem_cols;
+    int acc_stages;         // TMEM accumulator stages (2, or 1 when 2*BN columns would leave no room for a second CTA)
     int is_fp16;
     int* err;
 };
@@ -104,15 +130,15 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
         if (i < P.nprob && t >= P.prob[i].tile_begin) pi = i;
     const IgemmProblem& q = P.prob[pi];
     const int local = t - q.tile_begin;
-    const int nt = local % q.n_tiles;
-    const int mt = local / q.n_tiles;
+    const int mt = (int)fdiv((uint32_t)local, q.fd_n_tiles);
+    const int nt = local - mt * q.n_tiles;
     tc.pi = pi;
-    tc.b = mt / q.tiles_per_img;
+    tc.b = (int)fdiv((uint32_t)mt, q.fd_tiles_per_img);
     const int r = mt - tc.b * q.tiles_per_img;
-    const int tyi = r / q.tiles_x;
+    const int tyi = (int)fdiv((uint32_t)r, q.fd_tiles_x);
     tc.y0 = tyi * P.TH;
-    tc.x0 = (r - tyi * q.tiles_x) * P.TW;
-    tc.n0 = nt * P.BN;
+    tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode == AMODE_DXN ? 1 : 0);   // DXN: slab column 0 is the left halo
+    tc.n0 = nt * P.n_out;
     return tc;
 }
 
@@ -173,7 +199,8 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             }
         } else {
             int step = 0;
-            for (int dc = 0; dc < 3 * q.nchunk; ++dc) {                       // (dx, channel chunk)
+            const int ndc = (P.amode == AMODE_SLAB ? 3 : 1) * q.nchunk;
+            for (int dc = 0; dc < ndc; ++dc) {                                // SLAB: (dx, channel chunk); DXN: channel chunk
                 ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
                 const uint32_t a_lo = a_base + ia * a_slot16;
 #pragma unroll
@@ -192,12 +219,11 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             }
         }
         ptx::umma_commit(&tmem_full_bar[acc]);                                // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
 }
 
-__global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
+__global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
     __shared__ __align__(8) uint64_t full_b[IGEMM_MAX_SLOTS], empty_b[IGEMM_MAX_SLOTS];
@@ -206,6 +232,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[2][256];
     __shared__ __align__(16) float s_vec[256];
+    __shared__ float s_dot[2][128], s_dot2[2][128];          // partial / full per-pixel dot products (gate, out_conv)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -227,7 +254,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
         ptx::mbar_init(&c_load_bar, 1);
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 4);     // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[a], 8);     // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
     }
@@ -236,7 +263,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
         ptx::tmem_relinquish();
     }
     if (threadIdx.x >= 64 && P.prob[0].vec != nullptr)                        // GATE / OUTCONV vector, constant per launch
-        for (int i = threadIdx.x - 64; i < P.BN; i += 128) s_vec[i] = P.prob[0].vec[i];
+        for (int i = threadIdx.x - 64; i < P.n_out; i += 256) s_vec[i] = P.prob[0].vec[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -251,7 +278,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
             if (res) {                                                        // whole weight matrix once per CTA
                 const IgemmProblem& q = P.prob[0];
                 const int cin = q.nchunk * P.KC;
-                const int steps = q.taps * q.nchunk;
+                const int steps = (P.amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
                 ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
                 for (int s = 0; s < steps; ++s) {
                     int kcoord = s * P.KC;                                    // TAP order: (tap, chunk)
@@ -259,6 +286,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                         const int dyi = s % 3, dc = s / 3;
                         const int dxi = dc / q.nchunk, ch = dc - dxi * q.nchunk;
                         kcoord = (dyi * 3 + dxi) * cin + ch * P.KC;
+                    } else if (P.amode == AMODE_DXN) {                        // DXN order: (chunk, dy); K' = (dy, Cin)
+                        const int dyi = s % 3, ch = s / 3;
+                        kcoord = dyi * cin + ch * P.KC;
                     }
                     ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, 0);
                 }
@@ -287,17 +317,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                 } else {
                     const int cin = q.nchunk * P.KC;
                     const uint32_t slab_bytes = (uint32_t)((P.TH + 2) * P.TW * P.KC * 2);
-                    for (int dxi = 0; dxi < 3; ++dxi) {
+                    const bool dxn = P.amode == AMODE_DXN;
+                    for (int dxi = 0; dxi < (dxn ? 1 : 3); ++dxi) {
                         for (int ch = 0; ch < q.nchunk; ++ch) {
                             ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                             ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
-                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
+                                             dxn ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
                             if (++ia == P.nA) { ia = 0; pa ^= 1; }
                             if (!res) {
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                                     ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
-                                    ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], (dyi * 3 + dxi) * cin + ch * P.KC, tc.n0);
+                                    ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
+                                                     dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC, dxn ? 0 : tc.n0);
                                     if (++ib == P.nB) { ib = 0; pb ^= 1; }
                                 }
                             }
@@ -314,10 +347,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
             else                 mma_role<1>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
         }
     } else {
-        // =========================== epilogue (warps 2..5) ===========================
-        const int quarter = warp & 3;                           // TMEM lane quarter this warp may read
+        // =========================== epilogue (warps 2..9) ===========================
+        // Two warps per TMEM lane quarter (warp % 4): group 0 = warps 2..5, group 1 = warps 6..9.  A pixel row is
+        // owned by one thread of each group; the two split the channel range, so every scheduler has two epilogue
+        // warps to overlap (the epilogue, not the tensor pipe, limits the small-N layers: profiles/r01_ncu_dxn*).
+        const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        const int etid = threadIdx.x - 64;                      // 0..127
+        const int etid = threadIdx.x - 64;                      // 0..255
         const int ty = row >> P.tw_shift;
         const int tx = row & (P.TW - 1);
         const int f16 = P.is_fp16;
@@ -327,42 +364,109 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
         uint32_t acc_phase = 0;
         int cslot = 0;
         uint32_t c_phase = 0;
+        int par = 1;                                            // parity of the tile iteration: double-buffers s_bias / s_dot
         for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+            par ^= 1;
             const TileCoord tc = decode_tile(P, t);
             const IgemmProblem& q = P.prob[tc.pi];
             const int y = tc.y0 + ty, x = tc.x0 + tx;
             const bool valid = (y < q.H) && (x < q.W);
             // stage this tile's bias in shared memory (double-buffered by accumulator parity)
-            {
+            if (etid < P.n_out) {
                 const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
-                float* sb = s_bias[acc];
-                if (q.epi == EPI_CONVT) {
-                    for (int i = etid; i < P.BN; i += 128) sb[i] = __ldg(bsrc + (tc.n0 + i) % q.convt_cout);
-                } else {
-                    for (int i = etid; i < P.BN; i += 128) sb[i] = __ldg(bsrc + tc.n0 + i);
-                }
+                s_bias[par][etid] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + etid) % q.convt_cout : tc.n0 + etid));
             }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
             ptx::tc_fence_after();
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // bias visible to the four epilogue warps
-            const float* sb = s_bias[acc];
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // bias visible to the eight epilogue warps
+            const float* sb = s_bias[par];
             const uint32_t taddr = tmem_base + (uint32_t)(acc * P.BN) + ((uint32_t)(quarter * 32) << 16);
 
-            if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+            if (P.amode == AMODE_DXN) {
+                // ---- combine the three dx column groups: out[p] = E0[p-1] + E1[p] + E2[p+1]  (p = lane = slab column)
+                const int N = P.n_out;
+                const bool inner = lane >= 1 && lane <= P.VW;                    // the 30 valid output columns
+                uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
+                if (q.epi == EPI_STORE) {
+                    if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                float dot = 0.f;
+                const int srow = quarter * P.VW + lane - 1;                      // row inside the (CB, VW, TH) store box
+                for (int c0 = grp * 16; c0 < N; c0 += 32) {                      // 16-channel chunks alternate between the groups
+                    uint32_t e0[32], e1[32], e2[32];
+                    ptx::tmem_ld_32x16(taddr + c0, e0);
+                    ptx::tmem_ld_32x16(taddr + N + c0, e1);
+                    ptx::tmem_ld_32x16(taddr + 2 * N + c0, e2);
+                    ptx::tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = v * 4 + u;
+                            const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[i]), 1);
+                            const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[i]), 1);
+                            f[i] = fmaxf((l + __uint_as_float(e1[i])) + (r + bb[u]), 0.f);   // every DXN layer ends in ReLU
+                        }
+                    }
+                    if (q.epi == EPI_STORE) {
+                        if (inner) {
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                const uint4 o = make_uint4(pack2(f[v * 8 + 0], f[v * 8 + 1], f16), pack2(f[v * 8 + 2], f[v * 8 + 3], f16),
+                                                           pack2(f[v * 8 + 4], f[v * 8 + 5], f16), pack2(f[v * 8 + 6], f[v * 8 + 7], f16));
+                                uint32_t off = (uint32_t)(srow * c_pitch + (c0 + v * 8) * 2);
+                                off ^= ((off >> 7) & swz_mask) << 4;
+                                *reinterpret_cast<uint4*>(cs + off) = o;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
+                            dot = fmaf(f[v * 4 + 0], w4.x, dot);
+                            dot = fmaf(f[v * 4 + 1], w4.y, dot);
+                            dot = fmaf(f[v * 4 + 2], w4.z, dot);
+                            dot = fmaf(f[v * 4 + 3], w4.w, dot);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (q.epi == EPI_STORE) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (etid == 0) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    cslot ^= 1;
+                } else {
+                    if (grp == 1) s_dot[par][row] = dot;                         // partial dot of the odd chunks
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (grp == 0 && inner && valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + s_dot[par][row] + q.scalar;
+                }
+            } else if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+                const int piece = P.CB >= 32 ? (P.CB >> 1) : P.CB;               // columns per thread per store group
                 for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
                     // the TMA store that used this staging slot two groups ago must have finished reading it
                     if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
-                    for (int cc = 0; cc < P.CB; cc += 32) {
+                    const int cc = grp * piece;                                  // group 1 takes the upper half of the group
+                    if (cc < P.CB) {
                         uint32_t r[32];
-                        const int ncol = min(32, P.CB - cc);
-                        if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
-                        else            ptx::tmem_ld_32x16(taddr + c0 + cc, r);
+                        if (piece == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
+                        else             ptx::tmem_ld_32x16(taddr + c0 + cc, r);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            if (v * 8 < ncol) {
+                            if (v * 8 < piece) {
                                 const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8);
                                 const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8 + 4);
                                 float f[8];
@@ -387,7 +491,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (etid == 0) {
                         const int n = tc.n0 + c0;
                         const void* tm;
@@ -401,37 +505,40 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                     cslot ^= 1;
                 }
             } else {
-                // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel
+                // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel;
+                // 16-channel chunks alternate between the two warp groups, partial sums meet in shared memory
                 float dot = 0.f;
-                for (int c0 = 0; c0 < P.BN; c0 += 32) {
+                for (int c0 = grp * 16; c0 < P.BN; c0 += 32) {
                     uint32_t r[32];
-                    const int ncol = min(32, P.BN - c0);
-                    if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0, r);
-                    else            ptx::tmem_ld_32x16(taddr + c0, r);
+                    ptx::tmem_ld_32x16(taddr + c0, r);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) {
-                        if (v * 4 < ncol) {
-                            const float4 b = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
-                            const float4 w = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
-                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 0]) + b.x, 0.f), w.x, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 1]) + b.y, 0.f), w.y, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 2]) + b.z, 0.f), w.z, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 3]) + b.w, 0.f), w.w, dot);
-                        }
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 b = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
+                        const float4 w = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
+                        dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 0]) + b.x, 0.f), w.x, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 1]) + b.y, 0.f), w.y, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 2]) + b.z, 0.f), w.z, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 3]) + b.w, 0.f), w.w, dot);
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (grp == 1) s_dot[par][row] = dot;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (grp == 0) dot += s_dot[par][row];                             // group 0 now holds the full sum
                 if (q.epi == EPI_OUTCONV) {
-                    if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
+                    if (grp == 0 && valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 } else {
+                    if (grp == 0) s_dot2[par][row] = dot;                         // full pre-activation for the partner thread
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    dot = s_dot2[par][row];
                     const float a = 1.f / (1.f + expf(-(dot + q.scalar)));
                     const float scale = q.gate_plus_x ? (1.f + a) : a;
-                    if (valid && q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
+                    if (grp == 0 && valid && q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
                     // scale the skip tile in place: TMA load (L2 hit: the same bytes were just streamed in as the A
-                    // operand) -> multiply this thread's pixel row in shared memory -> TMA store, CB channels at a time
+                    // operand) -> multiply this thread's half of its pixel row in shared memory -> TMA store
                     for (int c0 = 0; c0 < q.gate_C; c0 += P.CB) {
                         uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
                         if (etid == 0) {
@@ -441,7 +548,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                         }
                         ptx::mbar_wait(&c_load_bar, c_phase, P.err, ERR_EPI_WAIT);
                         c_phase ^= 1;
-                        for (int v = 0; v < (c_pitch >> 4); ++v) {
+                        for (int v = grp; v < (c_pitch >> 4); v += 2) {
                             uint32_t off = (uint32_t)(row * c_pitch + v * 16);
                             off ^= ((off >> 7) & swz_mask) << 4;
                             uint4 val = *reinterpret_cast<uint4*>(cs + off);
@@ -453,7 +560,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                             *reinterpret_cast<uint4*>(cs + off) = val;
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
                         if (etid == 0) {
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                          ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
@@ -463,8 +570,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_tc_kernel(const __grid
                     }
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
         }
         if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores landed
     }
