@@ -42,7 +42,8 @@ struct KeySpec {
 
 struct GemmW {                // packed GEMM operand, device resident
     void* dB = nullptr;       // [N][K] 16-bit, K contiguous
-    void* dBdx = nullptr;     // 3x3 only, N in {16,32,64}: [3N][3Cin], row j*N+o = W[o][:][dy][dx=j] (AMODE_DXN)
+    void* dBdx = nullptr;     // 3x3 only, N in {16,32,64}: [3N][3Cin], row (h*3+j)*dx_nt+o' = W[h*dx_nt+o'][:][dy][dx=j] (AMODE_DXN)
+    int dx_nt = 0;            // output channels per dx-stacked tile (N, or N/2 so that one tile's weights fit in smem)
     float* dbias = nullptr;   // fp32
     float* dvec = nullptr;    // optional fp32 vector (gate w_psi, out_conv w)
     float scalar = 0.f;       // optional scalar (gate b_psi, out_conv b)
@@ -63,6 +64,7 @@ struct ConvDesc {             // one GEMM problem
     const float* bias_img = nullptr;
     int bias_img_stride = 0;
     View out;                 // STORE/CONVT destination, GATE: skip view (C = gate_C)
+    View pool_out;            // optional fused MaxPool2d(2) destination (dense NHWC), p == nullptr: none
     int convt_cout = 0;
     float* aux = nullptr;
     int gate_plus_x = 0;
@@ -114,6 +116,7 @@ struct Engine {
     int last_launches = 0;
     int opt_amode = -1;
     int opt_resident = 1;
+    int opt_fusepool = 1;
     int opt_ctas = 0;
     int opt_profile = 0;
     Plan* last_plan = nullptr;
@@ -280,14 +283,18 @@ static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::
     }
     int r = finish_gemm(e, g, Bm, bias);
     if (!r && taps == 9 && (cout == 16 || cout == 32 || cout == 64)) {
-        // horizontal taps stacked along N: Bd[j*cout + o][dy*cin + i] = W[o][i][dy][j] * s[o]
+        // horizontal taps stacked along N, in tiles of nt output channels whose 3*nt x 3*cin weights fit in smem:
+        // Bd[(h*3 + j)*nt + o'][dy*cin + i] = W[h*nt + o'][i][dy][j] * s[o]
+        int nt = cout;
+        while (nt > 16 && (size_t)3 * nt * 3 * cin * 2 > 112 * 1024) nt >>= 1;
+        g.dx_nt = nt;
         std::vector<uint16_t> bd((size_t)3 * cout * 3 * cin);
         const bool f16 = e.is_fp16();
         for (int j = 0; j < 3; ++j)
             for (int o = 0; o < cout; ++o)
                 for (int dy = 0; dy < 3; ++dy)
                     for (int i = 0; i < cin; ++i)
-                        bd[((size_t)j * cout + o) * 3 * cin + (size_t)dy * cin + i] =
+                        bd[((size_t)((o / nt) * 3 + j) * nt + (o % nt)) * 3 * cin + (size_t)dy * cin + i] =
                             to16((float)((double)(*w)[((size_t)o * cin + i) * 9 + dy * 3 + j] * s[o]), f16);
         uint16_t* d = nullptr;
         if (upload(e, bd, &d) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "weight upload failed");
@@ -512,21 +519,24 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     if (!BN) return e.fail(AAU_ERR_INVALID, "output channels must be a multiple of 16");
     if (d0.epi == EPI_GATE || d0.epi == EPI_OUTCONV)
         if (BN != Ntot) return e.fail(AAU_ERR_INVALID, "gate / out_conv epilogues need all channels in one tile");
+    const bool want_pool = d0.pool_out.p != nullptr && d0.epi == EPI_STORE && descs.size() == 1;
     const bool conv3 = d0.w->taps == 9;
     bool slab = conv3 && d0.dil == 1 && BN <= 128;
     if (e.opt_amode == 0) slab = false;
     if (e.opt_amode == 1 && conv3 && d0.dil == 1 && BN <= 128) slab = true;
     bool dxn = conv3 && d0.dil == 1 && descs.size() == 1 && d0.w->dBdx != nullptr && Ntot == BN &&
                (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 2);
+    if (dxn && d0.epi == EPI_OUTCONV && d0.w->dx_nt != Ntot) dxn = false;
+    int n_out = BN;
     if (dxn) {                                                     // does the dx-stacked pipeline fit in shared memory?
-        const int sw = P.KC * 2, a = 6 * 32 * sw, b = 3 * BN * sw, st = 3 * (Cin / P.KC);
-        const int rb = (st * b + 1023) & ~1023, cb = d0.epi == EPI_STORE ? 2 * 128 * BN * 2 : 0, budget1 = 225280;
-        const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * (a + 3 * b) <= budget1);
-        if (!fits) dxn = false;
+        n_out = d0.w->dx_nt;
+        const int sw = P.KC * 2, a = 6 * 32 * sw, b = 3 * n_out * sw, st = 3 * (Cin / P.KC);
+        const int rb = (st * b + 1023) & ~1023, cb = (d0.epi == EPI_STORE ? 2 * 128 * n_out * 2 : 0) + (want_pool ? 8192 : 0), budget1 = 225280;
+        const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * a + 4 * b <= budget1);
+        if (!fits) { dxn = false; n_out = BN; }
     }
     if (dxn) slab = true;                                          // shares the slab geometry code below
     P.amode = dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP);
-    const int n_out = BN;
     if (dxn) BN = 3 * n_out;                                       // MMA N: the three dx taps side by side
     P.BN = BN;
     P.n_out = n_out;
@@ -536,6 +546,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     for (int tw = 8; tw <= 128; tw <<= 1) {
         const int th = 128 / tw;
         if (slab && th < 4) continue;
+        if (want_pool && th < 2) continue;
         double cost = (double)((H + th - 1) / th * th) * ((W + tw - 1) / tw * tw);
         if (slab) cost *= 1.0 + 0.5 * 2.0 / th;     // halo rows cost bandwidth, not MMA time
         if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
@@ -554,13 +565,17 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.CB = cdiv % 64 == 0 ? 64 : (cdiv % 32 == 0 ? 32 : 16);
     if (d0.epi != EPI_GATE && n_out % P.CB) P.CB = 16;
     P.c_slot_bytes = 128 * P.CB * 2;
-    const int c_bytes = tma_out ? 2 * P.c_slot_bytes : 0;
+    P.pool = want_pool ? 1 : 0;
+    P.p_slot_bytes = want_pool ? ((((P.TH / 2) * (P.VW / 2) * P.CB * 2) + 1023) & ~1023) : 0;
+    const int c_bytes = tma_out ? 2 * (P.c_slot_bytes + P.p_slot_bytes) : 0;
     P.acc_stages = (BN > 128 && BN <= 256 && dxn) ? 1 : 2;        // dx-stacked N = 192: one stage, two CTAs overlap instead
     P.tmem_cols = 32;
     while (P.tmem_cols < P.acc_stages * BN) P.tmem_cols <<= 1;
     // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the
     // tensor pipe, so several CTAs share an SM there (TMEM: 512 columns per SM, registers: 3 x 192 threads fit).
-    const bool can_res = descs.size() == 1 && Ntot == n_out && e.opt_resident != 0;
+    // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
+    // n_tiles so that the static striding keeps every CTA on the same N tile
+    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn) && e.opt_resident != 0;
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
     int ctas = (BN <= 128 || P.acc_stages == 1) ? 2 : 1;          // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / P.tmem_cols);
@@ -573,12 +588,16 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             if (pass == 0 && !res) continue;
             const int fixed = c_bytes + (res ? res_bytes : 0);
             const int unit = res ? P.a_slot_bytes : (slab ? P.a_slot_bytes + 3 * P.b_slot_bytes : P.a_slot_bytes + P.b_slot_bytes);
-            const int n = (budget - fixed) / unit;
-            const int need = 2;
-            if (n < need) continue;
+            int n = (budget - fixed) / unit;
+            int nb = n * (slab ? 3 : 1);
+            if (n < 2 && !res && slab) {                           // tight fit: two slabs and whatever B slots remain (>= 4)
+                nb = (budget - fixed - 2 * P.a_slot_bytes) / P.b_slot_bytes;
+                n = nb >= 4 ? 2 : 0;
+            }
+            if (n < 2) continue;
             P.b_resident = res ? 1 : 0;
             P.nA = std::min((int)IGEMM_MAX_SLOTS, n);
-            P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, n * (slab ? 3 : 1));
+            P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, nb);
             ok = true;
         }
         if (ok) break;
@@ -652,6 +671,14 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             }
         }
     }
+    if (want_pool) {
+        const View& o = d0.pool_out;
+        const uint32_t pbox[4] = {(uint32_t)P.CB, (uint32_t)(P.VW / 2), (uint32_t)(P.TH / 2), 1u};
+        const uint64_t pdims[4] = {(uint64_t)Ntot, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)o.B};
+        const uint64_t pstr[3] = {(uint64_t)o.ld * 2, (uint64_t)o.W * o.ld * 2, (uint64_t)o.H * o.W * o.ld * 2};
+        if (!encode_map(e, &P.tmP, o.p + (size_t)o.choff * 2, 4, pdims, pstr, pbox, P.CB * 2))
+            return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a pooled output tensor");
+    }
     OpInfo oi;
     oi.name = name;
     oi.kernel = "igemm_tc_kernel";
@@ -660,6 +687,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         oi.flops += 2.0 * px * d.w->K * d.w->N;
         oi.bytes += px * d.in.C * 2 + (double)d.w->K * d.w->N * 2;
         if (d.epi == EPI_STORE) oi.bytes += px * d.w->N * 2;
+        if (d.pool_out.p) oi.bytes += px * d.w->N * 2 / 4;
         if (d.epi == EPI_CONVT) oi.bytes += px * d.w->N * 2;
         if (d.epi == EPI_GATE) { oi.bytes += px * d.out.C * 2; oi.flops += 2.0 * px * d.w->N; }
         if (d.epi == EPI_OUTCONV) { oi.bytes += px * 4; oi.flops += 2.0 * px * d.w->N; }
@@ -669,8 +697,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // NOTE: cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for this kernel at every shared-memory size
     // (it does not model TMEM), while two CTAs measurably co-reside (profiles/r01_ctas_experiment.md); if they did
     // not, the second half of the grid would simply run as a second wave over the same static tile striding.
-    const int grid = std::min(P.total_tiles, e.num_sms * ctas);
-    oi.name += " [" + std::string(dxn ? "dxn" : (slab ? "slab" : "tap")) + (P.b_resident ? ",Bres" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
+    int grid = std::min(P.total_tiles, e.num_sms * ctas);
+    if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
+    oi.name += " [" + std::string(dxn ? "dxn" : (slab ? "slab" : "tap")) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
                " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
@@ -739,12 +768,14 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
     if (e.has_aspp()) plan.named["asppcat"] = asppcat;
 
     int r;
-    auto conv = [&](const std::string& name, const View& in, const View& out, int dil = 1) -> int {
+    auto conv = [&](const std::string& name, const View& in, const View& out, const View* pooled = nullptr) -> int {
         ConvDesc d;
         d.w = &e.gw.at(name);
-        d.in = in; d.out = out; d.dil = dil; d.epi = EPI_STORE; d.relu = 1;
+        d.in = in; d.out = out; d.dil = 1; d.epi = EPI_STORE; d.relu = 1;
+        if (pooled) d.pool_out = *pooled;
         return add_igemm(e, plan, name, {d}, 0);
     };
+    const bool fuse_pool = e.opt_fusepool != 0;
     auto pool = [&](const View& in, const View& out) {
         const long long items = (long long)in.B * (in.H / 2) * (in.W / 2) * (in.C / 8);
         const int grid = ew_grid(e, items, 256);
@@ -776,14 +807,14 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             return cudaGetLastError();
         });
     }
-    if ((r = conv("d1.1", ta[1], sub_view(cat[1], 0, ch[1])))) return r;
+    if ((r = conv("d1.1", ta[1], sub_view(cat[1], 0, ch[1]), fuse_pool ? &pl[1] : nullptr))) return r;
     for (int l = 2; l <= 4; ++l) {
-        pool(sub_view(cat[l - 1], 0, ch[l - 1]), pl[l - 1]);
+        if (!fuse_pool) pool(sub_view(cat[l - 1], 0, ch[l - 1]), pl[l - 1]);
         const std::string p = "d" + std::to_string(l);
         if ((r = conv(p + ".0", pl[l - 1], ta[l]))) return r;
-        if ((r = conv(p + ".1", ta[l], sub_view(cat[l], 0, ch[l])))) return r;
+        if ((r = conv(p + ".1", ta[l], sub_view(cat[l], 0, ch[l]), fuse_pool ? &pl[l] : nullptr))) return r;
     }
-    pool(sub_view(cat[4], 0, ch[4]), pl[4]);
+    if (!fuse_pool) pool(sub_view(cat[4], 0, ch[4]), pl[4]);
     // ---- bridge
     if (e.has_aspp()) {
         {
@@ -1158,8 +1189,8 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         h->e.last_plan = nullptr;
         return AAU_OK;
     }
-    if (std::string(name) == "resident" || std::string(name) == "ctas") {
-        (std::string(name) == "resident" ? h->e.opt_resident : h->e.opt_ctas) = value;
+    if (std::string(name) == "resident" || std::string(name) == "ctas" || std::string(name) == "fusepool") {
+        (std::string(name) == "resident" ? h->e.opt_resident : (std::string(name) == "ctas" ? h->e.opt_ctas : h->e.opt_fusepool)) = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

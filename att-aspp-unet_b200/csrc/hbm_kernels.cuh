@@ -75,17 +75,6 @@ __global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restric
 // ---------------------------------------------------------------------------------------------------------
 // MaxPool2d(2) with floor semantics (attention_aspp_unet_pipeline_stage.py:115-118): the last odd row/column is
 // never read.  One thread = one output pixel x 8 channels.
-__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_fp16) {
-    if (is_fp16) {
-        __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-        return *reinterpret_cast<uint32_t*>(&r);
-    }
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
-__device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int f) {
-    return make_uint4(max2(a.x, b.x, f), max2(a.y, b.y, f), max2(a.z, b.z, f), max2(a.w, b.w, f));
-}
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const uint8_t* __restrict__ in, int in_ld, int in_choff, int B, int H, int W, int C,
                                                          uint8_t* __restrict__ out, int is_fp16) {
     const int OH = H >> 1, OW = W >> 1, CV = C >> 3;

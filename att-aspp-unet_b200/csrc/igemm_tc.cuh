@@ -90,6 +90,7 @@ struct alignas(64) IgemmProblem {
 struct alignas(64) IgemmParams {
     IgemmProblem prob[IGEMM_MAX_PROBLEMS];
     CUtensorMap tmC[4];     // output maps: STORE -> one per problem; CONVT -> one per (a,b) of the single problem
+    CUtensorMap tmP;        // fused MaxPool2d(2) output (pool != 0, single-problem STORE launches)
     int nprob, total_tiles;
     int amode;              // AMODE_*
     int KC;                 // channels per sub-block (16 / 32 / 64)
@@ -99,6 +100,7 @@ struct alignas(64) IgemmParams {
     int VW;                 // valid output columns per tile (== TW except DXN: TW - 2)
     int nA, nB, b_resident; // ring depths; b_resident: nB == number of k-steps and B is loaded once
     int a_slot_bytes, b_slot_bytes, c_slot_bytes;
+    int pool, p_slot_bytes; // fused 2x2 max-pool of the stored tile (floor semantics), its staging slot size
     int b_region_bytes;     // nB * b_slot_bytes rounded up to 1024 (the staging tiles behind it need that alignment)
     int tmem_cols;
     int acc_stages;         // TMEM accumulator stages (2, or 1 when 2*BN columns would leave no room for a second CTA)
@@ -120,6 +122,17 @@ __device__ __forceinline__ float2 unpack2(uint32_t v, int is_fp16) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
 }
 
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_fp16) {
+    if (is_fp16) {
+        __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int f) {
+    return make_uint4(max2(a.x, b.x, f), max2(a.y, b.y, f), max2(a.z, b.z, f), max2(a.w, b.w, f));
+}
 struct TileCoord { int pi, b, y0, x0, n0; };
 
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
@@ -140,6 +153,31 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
     tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode == AMODE_DXN ? 1 : 0);   // DXN: slab column 0 is the left halo
     tc.n0 = nt * P.n_out;
     return tc;
+}
+
+
+// MaxPool2d(2) of a staged output tile (rows = th x vw pixels, c_pitch bytes each, TMA-swizzled) into a staged
+// pooled tile ((th/2) x (vw/2) pixels, same pitch / swizzle).  One 16-byte vector (8 channels) per thread-iteration.
+__device__ __forceinline__ void pool_staged_tile(const uint8_t* cs, uint8_t* ps, int th, int vw, int c_pitch, uint32_t swz_mask,
+                                                 int etid, int f16) {
+    const int PW = vw >> 1, PH = th >> 1, cv = c_pitch >> 4;
+    for (int it = etid; it < PW * PH * cv; it += 256) {
+        const int v = it % cv, pp = it / cv;
+        const int py = pp / PW, px = pp - py * PW;
+        const int r00 = (2 * py) * vw + 2 * px;
+        uint4 m;
+        {
+            uint32_t o0 = (uint32_t)(r00 * c_pitch + v * 16), o1 = o0 + (uint32_t)c_pitch;
+            uint32_t o2 = o0 + (uint32_t)(vw * c_pitch), o3 = o2 + (uint32_t)c_pitch;
+            o0 ^= ((o0 >> 7) & swz_mask) << 4; o1 ^= ((o1 >> 7) & swz_mask) << 4;
+            o2 ^= ((o2 >> 7) & swz_mask) << 4; o3 ^= ((o3 >> 7) & swz_mask) << 4;
+            m = max8(max8(*reinterpret_cast<const uint4*>(cs + o0), *reinterpret_cast<const uint4*>(cs + o1), f16),
+                     max8(*reinterpret_cast<const uint4*>(cs + o2), *reinterpret_cast<const uint4*>(cs + o3), f16), f16);
+        }
+        uint32_t po = (uint32_t)(pp * c_pitch + v * 16);
+        po ^= ((po >> 7) & swz_mask) << 4;
+        *reinterpret_cast<uint4*>(ps + po) = m;
+    }
 }
 
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + (size_t)P.nA * P.a_slot_bytes;
     uint8_t* smem_c = smem_b + (size_t)P.b_region_bytes;
+    uint8_t* smem_p = smem_c + 2 * (size_t)P.c_slot_bytes;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.nprob; ++i) {
@@ -290,7 +329,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         const int dyi = s % 3, ch = s / 3;
                         kcoord = dyi * cin + ch * P.KC;
                     }
-                    ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, 0);
+                    ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)(blockIdx.x % q.n_tiles) * P.BN);
                 }
             }
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
@@ -330,7 +369,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                     ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                                     ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
                                     ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
-                                                     dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC, dxn ? 0 : tc.n0);
+                                                     dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC,
+                                                     dxn ? (tc.n0 / P.n_out) * P.BN : tc.n0);
                                     if (++ib == P.nB) { ib = 0; pb ^= 1; }
                                 }
                             }
@@ -440,9 +480,18 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 if (q.epi == EPI_STORE) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, 256;" ::: "memory");
+                    uint8_t* ps = smem_p + (size_t)cslot * P.p_slot_bytes;
+                    if (P.pool) {
+                        pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                     if (etid == 0) {
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
+                                     ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(tc.n0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
+                        if (P.pool)
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     cslot ^= 1;
@@ -492,6 +541,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, 256;" ::: "memory");
+                    uint8_t* ps = smem_p + (size_t)cslot * P.p_slot_bytes;
+                    if (P.pool) {
+                        pool_staged_tile(cs, ps, P.TH, P.TW, c_pitch, swz_mask, etid, f16);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                     if (etid == 0) {
                         const int n = tc.n0 + c0;
                         const void* tm;
@@ -500,6 +555,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                      ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                        if (P.pool)
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"(tc.x0 >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     cslot ^= 1;
