@@ -568,7 +568,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.pool = want_pool ? 1 : 0;
     P.p_slot_bytes = want_pool ? ((((P.TH / 2) * (P.VW / 2) * P.CB * 2) + 1023) & ~1023) : 0;
     const int c_bytes = tma_out ? 2 * (P.c_slot_bytes + P.p_slot_bytes) : 0;
-    P.acc_stages = (BN > 128 && BN <= 256 && dxn) ? 1 : 2;        // dx-stacked N = 192: one stage, two CTAs overlap instead
+    P.acc_stages = 2;                                             // epilogue group g drains stage g
     P.tmem_cols = 32;
     while (P.tmem_cols < P.acc_stages * BN) P.tmem_cols <<= 1;
     // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the

@@ -25,7 +25,7 @@
 //   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..9 = epilogue (two warps per TMEM lane quarter warp_id % 4, splitting the channel range).  Two accumulator stages in TMEM let the
+// warps 2..5 / 6..9 = two epilogue groups (one warp per TMEM lane quarter), group g drains accumulator stage g.  Two accumulator stages in TMEM let the
 // epilogue of tile i overlap the MMAs of tile i+1; small-N layers additionally run 2-3 CTAs per SM, because
 // there the single issuing thread (not the tensor pipe) is the limiter (ncu, profiles/r01_*).
 //
@@ -161,7 +161,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
 __device__ __forceinline__ void pool_staged_tile(const uint8_t* cs, uint8_t* ps, int th, int vw, int c_pitch, uint32_t swz_mask,
                                                  int etid, int f16) {
     const int PW = vw >> 1, PH = th >> 1, cv = c_pitch >> 4;
-    for (int it = etid; it < PW * PH * cv; it += 256) {
+    for (int it = etid; it < PW * PH * cv; it += 128) {           // 128 threads per epilogue group
         const int v = it % cv, pp = it / cv;
         const int py = pp / PW, px = pp - py * PW;
         const int r00 = (2 * py) * vw + 2 * px;
@@ -265,12 +265,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
     __shared__ __align__(8) uint64_t full_b[IGEMM_MAX_SLOTS], empty_b[IGEMM_MAX_SLOTS];
-    __shared__ __align__(8) uint64_t b_res_bar, c_load_bar;
+    __shared__ __align__(8) uint64_t b_res_bar, c_load_bar[2];
     __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float s_bias[2][256];
+    __shared__ __align__(16) float s_bias[2][2][256];       // [epilogue group][tile parity][channel]
     __shared__ __align__(16) float s_vec[256];
-    __shared__ float s_dot[2][128], s_dot2[2][128];          // partial / full per-pixel dot products (gate, out_conv)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -290,10 +289,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         if (!P.b_resident)
             for (int s = 0; s < P.nB; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
         ptx::mbar_init(&b_res_bar, 1);
-        ptx::mbar_init(&c_load_bar, 1);
+        ptx::mbar_init(&c_load_bar[0], 1);
+        ptx::mbar_init(&c_load_bar[1], 1);
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 8);     // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[a], 4);     // one arrive per epilogue warp of the owning group
         }
         ptx::fence_mbar_init();
     }
@@ -388,52 +388,59 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         }
     } else {
         // =========================== epilogue (warps 2..9) ===========================
-        // Two warps per TMEM lane quarter (warp % 4): group 0 = warps 2..5, group 1 = warps 6..9.  A pixel row is
-        // owned by one thread of each group; the two split the channel range, so every scheduler has two epilogue
-        // warps to overlap (the epilogue, not the tensor pipe, limits the small-N layers: profiles/r01_ncu_dxn*).
+        // Two independent epilogue groups of four warps (one warp per TMEM lane quarter, warp % 4): group g drains
+        // accumulator stage g, i.e. every second tile of this CTA.  Per tile the epilogue is a latency chain
+        // (tmem wait -> tcgen05.ld -> math -> smem -> proxy fence -> barrier -> TMA store), not a throughput problem
+        // (ncu: profiles/r01_ncu_dxn_summary.txt), so two chains in flight per CTA (x 2 CTAs per SM) is what pays.
         const int quarter = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        const int etid = threadIdx.x - 64;                      // 0..255
+        const int etid = (threadIdx.x - 64) & 127;              // 0..127 inside the group
         const int ty = row >> P.tw_shift;
         const int tx = row & (P.TW - 1);
         const int f16 = P.is_fp16;
         const int c_pitch = P.CB * 2;                           // bytes per staged row == store swizzle width
         const uint32_t swz_mask = (uint32_t)(c_pitch >> 4) - 1; // 7 / 3 / 1 for 128 / 64 / 32-byte swizzle
-        int acc = 0;
+        const int acc = grp;
         uint32_t acc_phase = 0;
-        int cslot = 0;
         uint32_t c_phase = 0;
-        int par = 1;                                            // parity of the tile iteration: double-buffers s_bias / s_dot
-        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-            par ^= 1;
+        uint8_t* cs = smem_c + (size_t)grp * P.c_slot_bytes;    // this group's staging tile
+        uint8_t* ps = smem_p + (size_t)grp * P.p_slot_bytes;    // ... and pooled staging tile
+        int par = 1;                                            // parity of this group's tile iteration
+        uint64_t* cbar = &c_load_bar[grp];
+        // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
+#define EPI_BAR()                                                      \
+    do {                                                               \
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   \
+        else          asm volatile("bar.sync 2, 128;" ::: "memory");   \
+    } while (0)
+        for (int t = blockIdx.x + grp * gridDim.x; t < P.total_tiles; t += 2 * gridDim.x) {
             const TileCoord tc = decode_tile(P, t);
             const IgemmProblem& q = P.prob[tc.pi];
             const int y = tc.y0 + ty, x = tc.x0 + tx;
             const bool valid = (y < q.H) && (x < q.W);
-            // stage this tile's bias in shared memory (double-buffered by accumulator parity)
-            if (etid < P.n_out) {
+            // bias of this tile, double-buffered by iteration parity (a slow thread may still read the previous one)
+            par ^= 1;
+            float* sb = s_bias[grp][par];
+            {
                 const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
-                s_bias[par][etid] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + etid) % q.convt_cout : tc.n0 + etid));
+                for (int i = etid; i < P.n_out; i += 128)
+                    sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout : tc.n0 + i));
             }
+            if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my previous stores have left smem
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
+            acc_phase ^= 1;
             ptx::tc_fence_after();
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // bias visible to the eight epilogue warps
-            const float* sb = s_bias[par];
+            EPI_BAR();                                          // bias visible, staging tiles free
             const uint32_t taddr = tmem_base + (uint32_t)(acc * P.BN) + ((uint32_t)(quarter * 32) << 16);
 
             if (P.amode == AMODE_DXN) {
                 // ---- combine the three dx column groups: out[p] = E0[p-1] + E1[p] + E2[p+1]  (p = lane = slab column)
                 const int N = P.n_out;
                 const bool inner = lane >= 1 && lane <= P.VW;                    // the 30 valid output columns
-                uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
-                if (q.epi == EPI_STORE) {
-                    if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
                 float dot = 0.f;
                 const int srow = quarter * P.VW + lane - 1;                      // row inside the (CB, VW, TH) store box
-                for (int c0 = grp * 16; c0 < N; c0 += 32) {                      // 16-channel chunks alternate between the groups
+                for (int c0 = 0; c0 < N; c0 += 16) {
                     uint32_t e0[32], e1[32], e2[32];
                     ptx::tmem_ld_32x16(taddr + c0, e0);
                     ptx::tmem_ld_32x16(taddr + N + c0, e1);
@@ -479,12 +486,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                 if (q.epi == EPI_STORE) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    uint8_t* ps = smem_p + (size_t)cslot * P.p_slot_bytes;
+                    EPI_BAR();
                     if (P.pool) {
                         pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        EPI_BAR();
                     }
                     if (etid == 0) {
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -494,28 +500,24 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                          ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    cslot ^= 1;
-                } else {
-                    if (grp == 1) s_dot[par][row] = dot;                         // partial dot of the odd chunks
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (grp == 0 && inner && valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + s_dot[par][row] + q.scalar;
+                } else if (inner && valid) {
+                    q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 }
             } else if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
-                const int piece = P.CB >= 32 ? (P.CB >> 1) : P.CB;               // columns per thread per store group
                 for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
-                    // the TMA store that used this staging slot two groups ago must have finished reading it
-                    if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
-                    const int cc = grp * piece;                                  // group 1 takes the upper half of the group
-                    if (cc < P.CB) {
+                    if (c0 > 0) {                                               // reuse of the staging tile inside one accumulator
+                        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        EPI_BAR();
+                    }
+                    for (int cc = 0; cc < P.CB; cc += 32) {
                         uint32_t r[32];
-                        if (piece == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
-                        else             ptx::tmem_ld_32x16(taddr + c0 + cc, r);
+                        const int ncol = min(32, P.CB - cc);
+                        if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
+                        else            ptx::tmem_ld_32x16(taddr + c0 + cc, r);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
-                            if (v * 8 < piece) {
+                            if (v * 8 < ncol) {
                                 const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8);
                                 const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8 + 4);
                                 float f[8];
@@ -540,12 +542,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    uint8_t* ps = smem_p + (size_t)cslot * P.p_slot_bytes;
+                    EPI_BAR();
                     if (P.pool) {
                         pool_staged_tile(cs, ps, P.TH, P.TW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        EPI_BAR();
                     }
                     if (etid == 0) {
                         const int n = tc.n0 + c0;
@@ -560,13 +561,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                          ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"(tc.x0 >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    cslot ^= 1;
                 }
             } else {
-                // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel;
-                // 16-channel chunks alternate between the two warp groups, partial sums meet in shared memory
+                // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel
                 float dot = 0.f;
-                for (int c0 = grp * 16; c0 < P.BN; c0 += 32) {
+                for (int c0 = 0; c0 < P.BN; c0 += 16) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x16(taddr + c0, r);
                     ptx::tmem_ld_wait();
@@ -583,30 +582,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
-                if (grp == 1) s_dot[par][row] = dot;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (grp == 0) dot += s_dot[par][row];                             // group 0 now holds the full sum
                 if (q.epi == EPI_OUTCONV) {
-                    if (grp == 0 && valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
+                    if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 } else {
-                    if (grp == 0) s_dot2[par][row] = dot;                         // full pre-activation for the partner thread
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    dot = s_dot2[par][row];
                     const float a = 1.f / (1.f + expf(-(dot + q.scalar)));
                     const float scale = q.gate_plus_x ? (1.f + a) : a;
-                    if (grp == 0 && valid && q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
+                    if (valid && q.aux) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = a;
                     // scale the skip tile in place: TMA load (L2 hit: the same bytes were just streamed in as the A
-                    // operand) -> multiply this thread's half of its pixel row in shared memory -> TMA store
+                    // operand) -> multiply this thread's pixel row in shared memory -> TMA store, CB channels at a time
                     for (int c0 = 0; c0 < q.gate_C; c0 += P.CB) {
-                        uint8_t* cs = smem_c + (size_t)cslot * P.c_slot_bytes;
                         if (etid == 0) {
-                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            ptx::mbar_expect_tx(&c_load_bar, (uint32_t)P.c_slot_bytes);
-                            ptx::tma_load_4d(cs, &P.tmC[0], &c_load_bar, c0, tc.x0, tc.y0, tc.b);
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            ptx::mbar_expect_tx(cbar, (uint32_t)P.c_slot_bytes);
+                            ptx::tma_load_4d(cs, &P.tmC[0], cbar, c0, tc.x0, tc.y0, tc.b);
                         }
-                        ptx::mbar_wait(&c_load_bar, c_phase, P.err, ERR_EPI_WAIT);
+                        ptx::mbar_wait(cbar, c_phase, P.err, ERR_EPI_WAIT);
                         c_phase ^= 1;
-                        for (int v = grp; v < (c_pitch >> 4); v += 2) {
+                        for (int v = 0; v < (c_pitch >> 4); ++v) {
                             uint32_t off = (uint32_t)(row * c_pitch + v * 16);
                             off ^= ((off >> 7) & swz_mask) << 4;
                             uint4 val = *reinterpret_cast<uint4*>(cs + off);
@@ -618,18 +610,17 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                             *reinterpret_cast<uint4*>(cs + off) = val;
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        EPI_BAR();
                         if (etid == 0) {
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                          ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
-                        cslot ^= 1;
                     }
                 }
             }
-            if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
         }
+#undef EPI_BAR
         if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores landed
     }
 
