@@ -117,6 +117,8 @@ struct Engine {
     int opt_amode = -1;
     int opt_resident = 1;
     int opt_fusepool = 1;
+    int opt_slab_max_bn = 256;
+    int opt_mt = 2;
     int opt_ctas = 0;
     int opt_profile = 0;
     Plan* last_plan = nullptr;
@@ -521,9 +523,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         if (BN != Ntot) return e.fail(AAU_ERR_INVALID, "gate / out_conv epilogues need all channels in one tile");
     const bool want_pool = d0.pool_out.p != nullptr && d0.epi == EPI_STORE && descs.size() == 1;
     const bool conv3 = d0.w->taps == 9;
-    bool slab = conv3 && d0.dil == 1 && BN <= 128;
+    bool slab = conv3 && d0.dil == 1 && BN <= e.opt_slab_max_bn;
     if (e.opt_amode == 0) slab = false;
-    if (e.opt_amode == 1 && conv3 && d0.dil == 1 && BN <= 128) slab = true;
+    if (e.opt_amode == 1 && conv3 && d0.dil == 1 && BN <= e.opt_slab_max_bn) slab = true;
     bool dxn = conv3 && d0.dil == 1 && descs.size() == 1 && d0.w->dBdx != nullptr && Ntot == BN &&
                (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 2);
     if (dxn && d0.epi == EPI_OUTCONV && d0.w->dx_nt != Ntot) dxn = false;
@@ -553,12 +555,15 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     }
     P.VW = P.TW;
     if (dxn) { P.TW = 32; P.TH = 4; P.VW = 30; }
+    // two vertically stacked M-blocks per tile when the weights stream through the B ring (halves their L2->SM traffic)
+    P.MT = (slab && !dxn && BN <= 128 && d0.epi == EPI_STORE && e.opt_mt == 2 && (size_t)9 * Cin * BN * 2 > 112 * 1024 &&
+            H > P.TH) ? 2 : 1;
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
     const int nchunk = Cin / P.KC;
     const int steps = (dxn ? 3 : d0.w->taps) * nchunk;            // k-steps (one B sub-block each) per tile
     P.b_slot_bytes = BN * swz;
-    P.a_slot_bytes = slab ? (((P.TH + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
+    P.a_slot_bytes = slab ? (((P.TH * P.MT + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
     // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
     const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE;
     const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : n_out);
@@ -570,7 +575,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     const int c_bytes = tma_out ? 2 * (P.c_slot_bytes + P.p_slot_bytes) : 0;
     P.acc_stages = 2;                                             // epilogue group g drains stage g
     P.tmem_cols = 32;
-    while (P.tmem_cols < P.acc_stages * BN) P.tmem_cols <<= 1;
+    while (P.tmem_cols < P.acc_stages * BN * P.MT) P.tmem_cols <<= 1;
     // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the
     // tensor pipe, so several CTAs share an SM there (TMEM: 512 columns per SM, registers: 3 x 192 threads fit).
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
@@ -618,7 +623,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         // activations: (C, W, H, B)
         const uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)d.in.W, (uint64_t)d.in.H, (uint64_t)d.in.B};
         const uint64_t astr[3] = {(uint64_t)d.in.ld * 2, (uint64_t)d.in.W * d.in.ld * 2, (uint64_t)d.in.H * d.in.W * d.in.ld * 2};
-        const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH + 2 : P.TH), 1u};
+        const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH * P.MT + 2 : P.TH), 1u};
         if (!encode_map(e, &q.tmA, d.in.p + (size_t)d.in.choff * 2, 4, adims, astr, abox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
         const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
@@ -634,7 +639,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         q.scalar = d.w->scalar;
         q.H = H; q.W = W;
         q.tiles_x = (W + P.VW - 1) / P.VW;
-        q.tiles_per_img = q.tiles_x * ((H + P.TH - 1) / P.TH);
+        q.tiles_per_img = q.tiles_x * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
         q.m_tiles = d.in.B * q.tiles_per_img;
         q.n_tiles = Ntot / n_out;
         q.tile_begin = tile_begin;
@@ -700,7 +705,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     int grid = std::min(P.total_tiles, e.num_sms * ctas);
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
     oi.name += " [" + std::string(dxn ? "dxn" : (slab ? "slab" : "tap")) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
-               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + (P.MT == 2 ? " MT2" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
     plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
@@ -1191,6 +1196,12 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     }
     if (std::string(name) == "resident" || std::string(name) == "ctas" || std::string(name) == "fusepool") {
         (std::string(name) == "resident" ? h->e.opt_resident : (std::string(name) == "ctas" ? h->e.opt_ctas : h->e.opt_fusepool)) = value;
+        h->e.plans.clear();
+        h->e.last_plan = nullptr;
+        return AAU_OK;
+    }
+    if (std::string(name) == "slab_max_bn" || std::string(name) == "mt") {
+        (std::string(name) == "mt" ? h->e.opt_mt : h->e.opt_slab_max_bn) = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

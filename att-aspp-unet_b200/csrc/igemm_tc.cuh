@@ -21,6 +21,8 @@
 //                is one 32-pixel row of the tile; its 30 inner pixels are valid outputs, tiles overlap by two
 //                columns).  3x fewer MMAs and A loads -- what the small-N layers, which are limited by the
 //                shared-memory read of the A operand (64 cycles per MMA whatever N), need.
+//   With MT = 2 (SLAB, BN <= 128) a tile is two vertically adjacent 128-pixel blocks fed from one taller slab: every
+//   weight sub-block is used for two MMA groups, which halves the L2->SM weight traffic of the mid-size layers.
 // B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
 //   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
 //
@@ -95,6 +97,7 @@ struct alignas(64) IgemmParams {
     int amode;              // AMODE_*
     int KC;                 // channels per sub-block (16 / 32 / 64)
     int TW, TH, tw_shift;
+    int MT;                 // M-blocks (128 pixels each, stacked vertically) per tile sharing every B sub-block: 1, or 2 (SLAB, BN <= 128)
     int BN, CB;             // MMA N (DXN: 3*Cout); channels per TMA store (CB*2 bytes == the store swizzle width)
     int n_out;              // output channels per tile (== BN except DXN: BN / 3)
     int VW;                 // valid output columns per tile (== TW except DXN: TW - 2)
@@ -149,7 +152,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
     tc.b = (int)fdiv((uint32_t)mt, q.fd_tiles_per_img);
     const int r = mt - tc.b * q.tiles_per_img;
     const int tyi = (int)fdiv((uint32_t)r, q.fd_tiles_x);
-    tc.y0 = tyi * P.TH;
+    tc.y0 = tyi * P.TH * P.MT;
     tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode == AMODE_DXN ? 1 : 0);   // DXN: slab column 0 is the left halo
     tc.n0 = nt * P.n_out;
     return tc;
@@ -207,6 +210,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     const uint32_t b_base = lo_flags | ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4);
     const uint32_t a_slot16 = (uint32_t)P.a_slot_bytes >> 4, b_slot16 = (uint32_t)P.b_slot_bytes >> 4;
     const uint32_t a_dy16 = (uint32_t)(P.TW * swz) >> 4;                      // slab: next vertical tap = TW rows further
+    const uint32_t a_mb16 = (uint32_t)(P.TH * P.TW * swz) >> 4;               // slab: second M-block = TH image rows further
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     int acc = 0;
@@ -218,7 +222,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         const IgemmProblem& q = P.prob[tc.pi];
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN * P.MT);
         uint32_t accumulate = 0;
         if (P.amode == AMODE_TAP) {
             const int steps = q.taps * q.nchunk;
@@ -246,6 +250,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                     const int bslot = res ? step : ib;
                     if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
                     ptx::tc_fence_after();
+                    if (P.MT == 2) {                                          // second M-block: TH rows further down the slab
+                        uint32_t acc2 = accumulate;
+                        mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
+                    }
                     mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
                     if (!res) {
                         ptx::umma_commit(&empty_b[ib]);
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     }
                 } else {
                     const int cin = q.nchunk * P.KC;
-                    const uint32_t slab_bytes = (uint32_t)((P.TH + 2) * P.TW * P.KC * 2);
+                    const uint32_t slab_bytes = (uint32_t)((P.TH * P.MT + 2) * P.TW * P.KC * 2);
                     const bool dxn = P.amode == AMODE_DXN;
                     for (int dxi = 0; dxi < (dxn ? 1 : 3); ++dxi) {
                         for (int ch = 0; ch < q.nchunk; ++ch) {
@@ -432,7 +440,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
             acc_phase ^= 1;
             ptx::tc_fence_after();
             EPI_BAR();                                          // bias visible, staging tiles free
-            const uint32_t taddr = tmem_base + (uint32_t)(acc * P.BN) + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr0 = tmem_base + (uint32_t)(acc * P.BN * P.MT) + ((uint32_t)(quarter * 32) << 16);
+            uint32_t taddr = taddr0;
 
             if (P.amode == AMODE_DXN) {
                 // ---- combine the three dx column groups: out[p] = E0[p-1] + E1[p] + E2[p+1]  (p = lane = slab column)
@@ -504,8 +513,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 }
             } else if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+              for (int mb = 0; mb < P.MT; ++mb) {                               // M-blocks of the tile (vertically stacked)
+                taddr = taddr0 + (uint32_t)(mb * P.BN);
+                const int yb = tc.y0 + mb * P.TH;
                 for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
-                    if (c0 > 0) {                                               // reuse of the staging tile inside one accumulator
+                    if (c0 > 0 || mb > 0) {                                     // reuse of the staging tile inside one accumulator
                         if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         EPI_BAR();
                     }
@@ -536,7 +548,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                             }
                         }
                     }
-                    if (c0 + P.CB >= P.BN) {                                  // accumulator fully read: free the TMEM stage
+                    if (c0 + P.CB >= P.BN && mb == P.MT - 1) {                // accumulator fully read: free the TMEM stage
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -555,13 +567,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
                         else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0), "r"(yb), "r"(tc.b) : "memory");
                         if (P.pool)
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"(tc.x0 >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
+                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"(tc.x0 >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
+              }
             } else {
                 // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel
                 float dot = 0.f;
