@@ -119,6 +119,8 @@ struct Engine {
     int opt_fusepool = 1;
     int opt_slab_max_bn = 256;
     int opt_mt = 2;
+    int opt_cslots = 0;
+    int opt_rs = 1;
     int opt_ctas = 0;
     int opt_profile = 0;
     Plan* last_plan = nullptr;
@@ -537,8 +539,14 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * a + 4 * b <= budget1);
         if (!fits) { dxn = false; n_out = BN; }
     }
-    if (dxn) slab = true;                                          // shares the slab geometry code below
-    P.amode = dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP);
+    // row-shifted taps (AMODE_RS): small-N 3x3 layers whose whole weight matrix stays in shared memory and whose K is
+    // small enough that nine N-wide MMAs per 16 channels (32 + N/4 cycles each) stay under the HBM time of the tile
+    bool rs = conv3 && d0.dil == 1 && descs.size() == 1 && Ntot == BN && BN <= 64 && Cin <= Ntot && e.opt_rs != 0 &&
+              (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 3) && e.opt_resident != 0 &&
+              (size_t)9 * Cin * BN * 2 <= 112 * 1024;
+    if (rs) { dxn = false; n_out = BN; }
+    if (dxn || rs) slab = true;                                    // shares the slab geometry code below
+    P.amode = rs ? AMODE_RS : (dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP));
     if (dxn) BN = 3 * n_out;                                       // MMA N: the three dx taps side by side
     P.BN = BN;
     P.n_out = n_out;
@@ -554,9 +562,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
     }
     P.VW = P.TW;
-    if (dxn) { P.TW = 32; P.TH = 4; P.VW = 30; }
+    if (dxn || rs) { P.TW = 32; P.TH = 4; P.VW = 30; }
     // two vertically stacked M-blocks per tile when the weights stream through the B ring (halves their L2->SM traffic)
-    P.MT = (slab && !dxn && BN <= 128 && d0.epi == EPI_STORE && e.opt_mt == 2 && (size_t)9 * Cin * BN * 2 > 112 * 1024 &&
+    P.MT = (slab && !dxn && !rs && BN <= 128 && d0.epi == EPI_STORE && e.opt_mt == 2 && (size_t)9 * Cin * BN * 2 > 112 * 1024 &&
             H > P.TH) ? 2 : 1;
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
@@ -572,7 +580,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.c_slot_bytes = 128 * P.CB * 2;
     P.pool = want_pool ? 1 : 0;
     P.p_slot_bytes = want_pool ? ((((P.TH / 2) * (P.VW / 2) * P.CB * 2) + 1023) & ~1023) : 0;
-    const int c_bytes = tma_out ? 2 * (P.c_slot_bytes + P.p_slot_bytes) : 0;
+    int c_bytes = 0;                                              // staging tiles: cslots per epilogue group, chosen below
     P.acc_stages = 2;                                             // epilogue group g drains stage g
     P.tmem_cols = 32;
     while (P.tmem_cols < P.acc_stages * BN * P.MT) P.tmem_cols <<= 1;
@@ -588,9 +596,15 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     bool ok = false;
     for (; ctas >= 1 && !ok; --ctas) {
         const int budget = std::min(233472 / ctas - 7168, 232448 - 6144) - 1024;   // static smem + 1 KB driver reserve + alignment slack
-        for (int pass = 0; pass < 2 && !ok; ++pass) {
-            const bool res = pass == 0 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
-            if (pass == 0 && !res) continue;
+        // pass 0/1: weights resident, two / one staging tiles per epilogue group; pass 2/3: weights streamed, two / one
+        for (int pass = 0; pass < 4 && !ok; ++pass) {
+            const bool res = pass < 2 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
+            if (pass < 2 && !res) continue;
+            if (rs && !res) continue;                              // row-shifted taps index the resident weight matrix
+            const int cslots = (pass & 1) ? 1 : 2;
+            if (cslots == 2 && (!tma_out || e.opt_cslots == 1)) continue;
+            c_bytes = tma_out ? 2 * cslots * (P.c_slot_bytes + P.p_slot_bytes) : 0;
+            P.cslots = cslots;
             const int fixed = c_bytes + (res ? res_bytes : 0);
             const int unit = res ? P.a_slot_bytes : (slab ? P.a_slot_bytes + 3 * P.b_slot_bytes : P.a_slot_bytes + P.b_slot_bytes);
             int n = (budget - fixed) / unit;
@@ -599,7 +613,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
                 nb = (budget - fixed - 2 * P.a_slot_bytes) / P.b_slot_bytes;
                 n = nb >= 4 ? 2 : 0;
             }
-            if (n < 2) continue;
+            if (n < (cslots == 2 ? 3 : 2)) continue;               // a second staging tile must not starve the operand rings
             P.b_resident = res ? 1 : 0;
             P.nA = std::min((int)IGEMM_MAX_SLOTS, n);
             P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, nb);
@@ -704,8 +718,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // not, the second half of the grid would simply run as a second wave over the same static tile striding.
     int grid = std::min(P.total_tiles, e.num_sms * ctas);
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
-    oi.name += " [" + std::string(dxn ? "dxn" : (slab ? "slab" : "tap")) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
-               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) + (P.MT == 2 ? " MT2" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+    oi.name += " [" + std::string(rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap"))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots == 2 ? " c2" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
     plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
@@ -799,8 +813,9 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         const View o = ta[1];
         const float* w = e.d_stem_w;
         const float* b = e.d_stem_b;
-        const int grid = ew_grid(e, (long long)B * H * ((W + 1) / 2), 256);
-        const size_t smem = (size_t)10 * c * sizeof(float);
+        const int twc = std::min(256 / (c / 8), (int)STEM_MAX_TW);
+        const int tiles_x = (W + twc - 1) / twc, tiles_y = (H + STEM_TR - 1) / STEM_TR;
+        const int grid = (int)std::min<long long>((long long)B * tiles_x * tiles_y, (long long)e.num_sms * 2 * 4);
         OpInfo oi;
         oi.name = "d1.0";
         oi.kernel = "stem_conv3x3_kernel";
@@ -808,7 +823,8 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         oi.bytes = (double)B * H * W * (4 + 2.0 * c);     // fp32 frame in (1 byte when uint8) + NHWC out
         plan.info.push_back(oi);
         plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
-            stem_conv3x3_kernel<<<grid, 256, smem, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, f16);
+            if (f16) stem_conv3x3_kernel<true><<<grid, 256, 0, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, tiles_x, tiles_y);
+            else     stem_conv3x3_kernel<false><<<grid, 256, 0, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, tiles_x, tiles_y);
             return cudaGetLastError();
         });
     }
@@ -892,14 +908,15 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         if (fix) {
             const View in = tmpg[l];
             const long long items = (long long)B * Hs[l] * Ws[l] * (ch[l] / 8);
-            const int grid = ew_grid(e, items, 256);
+            const dim3 grid((unsigned)((Ws[l] * (ch[l] / 8) + 255) / 256), (unsigned)Hs[l], (unsigned)B);
             OpInfo oi;
             oi.name = p + ".up bilinear fix-up";
             oi.kernel = "resize_bilinear_kernel";
             oi.bytes = (double)items * 16 * 2;
             plan.info.push_back(oi);
             plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
-                resize_bilinear_kernel<<<grid, 256, 0, a.stream>>>(in.p, in.H, in.W, in.C, gdst.p, gdst.H, gdst.W, gdst.ld, gdst.choff, in.B, f16);
+                if (f16) resize_bilinear_kernel<true><<<grid, 256, 0, a.stream>>>(in.p, in.H, in.W, in.C, gdst.p, gdst.H, gdst.W, gdst.ld, gdst.choff, in.B);
+                else     resize_bilinear_kernel<false><<<grid, 256, 0, a.stream>>>(in.p, in.H, in.W, in.C, gdst.p, gdst.H, gdst.W, gdst.ld, gdst.choff, in.B);
                 return cudaGetLastError();
             });
         }
@@ -1200,8 +1217,14 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         h->e.last_plan = nullptr;
         return AAU_OK;
     }
-    if (std::string(name) == "slab_max_bn" || std::string(name) == "mt") {
-        (std::string(name) == "mt" ? h->e.opt_mt : h->e.opt_slab_max_bn) = value;
+    if (std::string(name) == "slab_max_bn" || std::string(name) == "mt" || std::string(name) == "cslots") {
+        (std::string(name) == "mt" ? h->e.opt_mt : (std::string(name) == "cslots" ? h->e.opt_cslots : h->e.opt_slab_max_bn)) = value;
+        h->e.plans.clear();
+        h->e.last_plan = nullptr;
+        return AAU_OK;
+    }
+    if (std::string(name) == "rs") {
+        h->e.opt_rs = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

@@ -16,58 +16,81 @@ namespace aau {
 __device__ __forceinline__ float load_px(const void* __restrict__ x, int x_dtype, long long idx) {
     return x_dtype == 0 ? __ldg((const float*)x + idx) : (float)__ldg((const uint8_t*)x + idx) / 255.0f;
 }
-// Two horizontally adjacent pixels per thread: the 9x4 weights of a 4-channel group are read from shared memory
-// as nine broadcast 16-byte loads and used for 72 FMAs, and the thread writes 2*C*2 contiguous bytes.
+// Tile = STEM_TR rows x (256 / (C/8)) columns of one frame.  The (halo-padded, already normalised) input tile sits in
+// shared memory; a thread owns ONE column and ONE group of 8 output channels, keeps its 9x8 folded weights in
+// registers and walks down the rows with a sliding 3x3 window (3 shared-memory reads + 72 FMAs per pixel).  The
+// C/8 threads of a pixel write its C*2 bytes back to back and a warp covers 32/(C/8) neighbouring pixels, so every
+// store instruction writes whole contiguous 128-byte lines.  HBM-bound: 1 byte in, 2*C bytes out per pixel.
+// uint8 input is normalised through a 256-entry table of float(v)/255.0f (one IEEE division per thread per block).
+enum { STEM_TR = 16, STEM_MAX_TW = 128 };
+template <bool F16>
 __global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restrict__ x, int x_dtype, int B, int H, int W,
                                                            const float* __restrict__ w9c,   // [9][C], BN scale folded in
                                                            const float* __restrict__ bias,  // [C]
-                                                           uint8_t* __restrict__ out, int out_ld, int out_choff, int C, int is_fp16) {
-    extern __shared__ __align__(16) float s_w[];      // [9][C] weights then [C] bias
-    for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) s_w[i] = i < 9 * C ? w9c[i] : bias[i - 9 * C];
-    __syncthreads();
-    const int Wp = (W + 1) >> 1;                                  // pixel pairs per row
-    const long long npair = (long long)B * H * Wp;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npair; p += (long long)gridDim.x * blockDim.x) {
-        const int xp = (int)(p % Wp);
-        const long long t = p / Wp;
-        const int y = (int)(t % H);
-        const long long b = t / H;
-        const int x0 = xp * 2;
-        const bool two = x0 + 1 < W;
-        float v[3][4];                                            // rows y-1..y+1, columns x0-1..x0+2
+                                                           uint8_t* __restrict__ out, int out_ld, int out_choff, int C,
+                                                           int tiles_x, int tiles_y) {
+    __shared__ float s_in[(STEM_TR + 2) * (STEM_MAX_TW + 2)];
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    const int CG = C >> 3;                                        // 8-channel groups per pixel
+    const int TWc = min(256 / CG, (int)STEM_MAX_TW);              // columns per tile
+    const int pitch = TWc + 2;
+    const uint32_t pitch_mul = ((1u << 20) + pitch - 1) / pitch;  // i / pitch == (i * pitch_mul) >> 20 for i < 2^11
+    const int cg = threadIdx.x % CG, col = threadIdx.x / CG;
+    float w[9][8], bz[8];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+    for (int t = 0; t < 9; ++t) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + t * C + cg * 8));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(w9c + t * C + cg * 8 + 4));
+        w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b4.x; w[t][5] = b4.y; w[t][6] = b4.z; w[t][7] = b4.w;
+    }
 #pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-                const int yy = y + ky - 1, xx = x0 + kx - 1;
-                v[ky][kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? load_px(x, x_dtype, (b * H + yy) * W + xx) : 0.f;
+    for (int i = 0; i < 8; ++i) bz[i] = __ldg(bias + cg * 8 + i);
+    const int per_img = tiles_x * tiles_y, ntiles = B * per_img;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / per_img, r0 = tile - b * per_img;
+        const int tyi = r0 / tiles_x, txi = r0 - tyi * tiles_x;
+        const int y0 = tyi * STEM_TR, x0 = txi * TWc;
+        __syncthreads();                                          // the previous tile has been consumed (and s_lut is written)
+        for (int i = threadIdx.x; i < (STEM_TR + 2) * pitch; i += 256) {
+            const int r = (int)(((uint32_t)i * pitch_mul) >> 20), cc = i - r * pitch;
+            const int yy = y0 + r - 1, xx = x0 + cc - 1;
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t idx = ((size_t)b * H + yy) * W + xx;
+                v = x_dtype == 0 ? __ldg((const float*)x + idx) : s_lut[__ldg((const uint8_t*)x + idx)];
             }
-        uint8_t* dst0 = out + ((((size_t)b * H + y) * W + x0) * out_ld + out_choff) * 2;
-        uint8_t* dst1 = dst0 + (size_t)out_ld * 2;
-        for (int c0 = 0; c0 < C; c0 += 8) {
-            float a0[8], a1[8];
+            s_in[i] = v;
+        }
+        __syncthreads();
+        if (col < TWc && x0 + col < W) {
+            float v[3][3];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a0[i] = a1[i] = s_w[9 * C + c0 + i];
+            for (int k = 0; k < 3; ++k) { v[0][k] = s_in[col + k]; v[1][k] = s_in[pitch + col + k]; }
+            uint8_t* dst = out + ((((size_t)b * H + y0) * W + x0 + col) * out_ld + out_choff + cg * 8) * 2;
+            const size_t row_bytes = (size_t)W * out_ld * 2;
+            const int nrow = min((int)STEM_TR, H - y0);
+#pragma unroll 3
+            for (int r = 0; r < nrow; ++r) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int k = 0; k < 3; ++k) v[2][k] = s_in[(r + 2) * pitch + col + k];
+                float a[8];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4 wa = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c0);
-                    const float4 wb = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * C + c0 + 4);
-                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                for (int i = 0; i < 8; ++i) a[i] = bz[i];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        a0[i] = fmaf(v[ky][kx], w[i], a0[i]);
-                        a1[i] = fmaf(v[ky][kx + 1], w[i], a1[i]);
-                    }
-                }
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a0[i] = fmaxf(a0[i], 0.f); a1[i] = fmaxf(a1[i], 0.f); }
-            *reinterpret_cast<uint4*>(dst0 + c0 * 2) = make_uint4(pack2(a0[0], a0[1], is_fp16), pack2(a0[2], a0[3], is_fp16),
-                                                                  pack2(a0[4], a0[5], is_fp16), pack2(a0[6], a0[7], is_fp16));
-            if (two)
-                *reinterpret_cast<uint4*>(dst1 + c0 * 2) = make_uint4(pack2(a1[0], a1[1], is_fp16), pack2(a1[2], a1[3], is_fp16),
-                                                                      pack2(a1[4], a1[5], is_fp16), pack2(a1[6], a1[7], is_fp16));
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a[i] = fmaf(v[ky][kx], w[ky * 3 + kx][i], a[i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.f);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(a[0], a[1], F16), pack2(a[2], a[3], F16),
+                                                            pack2(a[4], a[5], F16), pack2(a[6], a[7], F16));
+                dst += row_bytes;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { v[0][k] = v[1][k]; v[1][k] = v[2][k]; }
+            }
         }
     }
 }
@@ -175,43 +198,53 @@ __global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const float* __rest
 // floor-pooled skip is one row/column larger than the transposed-conv output
 // (attention_aspp_unet_pipeline_stage.py:106-107).  Index arithmetic follows ATen's upsample_bilinear2d:
 // scale = in/out, src = max(0, scale*(dst+0.5)-0.5), i0 = floor(src), i1 = min(i0+1, in-1), w1 = src-i0.
+// grid = (ceil(OW*C/8 / 256), OH, B): a thread produces 8 channels of one output pixel (16-byte vector).  An axis
+// whose size does not change has scale 1, so its second sample has weight exactly 0 and is neither read nor blended
+// (v*1 + u*0 == v for finite u): the usual one-axis fix-up is two reads (adjacent rows or pixels: L2 hits), eight
+// 2-term blends and one write per thread.  Instantiated per storage type so that unpack / pack are two instructions.
+template <bool F16>
+__device__ __forceinline__ void blend8(const uint4& p, const uint4& q, float wp, float wq, float (&o)[8]) {
+    const uint32_t a[4] = {p.x, p.y, p.z, p.w}, b[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 u = unpack2(a[k], F16), v = unpack2(b[k], F16);
+        o[2 * k] = wp * u.x + wq * v.x;
+        o[2 * k + 1] = wp * u.y + wq * v.y;
+    }
+}
+template <bool F16>
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __restrict__ in, int IH, int IW, int C,
                                                               uint8_t* __restrict__ out, int OH, int OW, int out_ld, int out_choff,
-                                                              int B, int is_fp16) {
+                                                              int B) {
     const int CV = C >> 3;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= OW * CV) return;
+    const int ox = i / CV, cv = i - ox * CV;
+    const int oy = blockIdx.y, b = blockIdx.z;
     const float sh = (float)IH / (float)OH, sw = (float)IW / (float)OW;
-    const long long total = (long long)B * OH * OW * CV;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % CV);
-        long long t = i / CV;
-        const int ox = (int)(t % OW);
-        t /= OW;
-        const int oy = (int)(t % OH);
-        const long long b = t / OH;
-        float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
-        const float wy1 = fy - (float)y0, wx1 = fx - (float)x0;
-        const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-        const uint8_t* base = in + (size_t)b * IH * IW * C * 2 + (size_t)cv * 16;
-        const uint4 q00 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x0) * C * 2));
-        const uint4 q01 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x1) * C * 2));
+    const float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
+    const float wy1 = fy - (float)y0, wx1 = fx - (float)x0;
+    const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    const uint8_t* base = in + (size_t)b * IH * IW * C * 2 + (size_t)cv * 16;
+    const uint4 q00 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x0) * C * 2));
+    float top[8], r[8];
+    if (IW != OW) blend8<F16>(q00, __ldg((const uint4*)(base + ((size_t)y0 * IW + x1) * C * 2)), wx0, wx1, top);
+    else          blend8<F16>(q00, q00, 1.f, 0.f, top);
+    if (IH != OH) {
         const uint4 q10 = __ldg((const uint4*)(base + ((size_t)y1 * IW + x0) * C * 2));
-        const uint4 q11 = __ldg((const uint4*)(base + ((size_t)y1 * IW + x1) * C * 2));
-        const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
-        const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
-        uint32_t o[4];
+        float bot[8];
+        if (IW != OW) blend8<F16>(q10, __ldg((const uint4*)(base + ((size_t)y1 * IW + x1) * C * 2)), wx0, wx1, bot);
+        else          blend8<F16>(q10, q10, 1.f, 0.f, bot);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 v00 = unpack2(a00[k], is_fp16), v01 = unpack2(a01[k], is_fp16);
-            const float2 v10 = unpack2(a10[k], is_fp16), v11 = unpack2(a11[k], is_fp16);
-            const float rx = wy0 * (wx0 * v00.x + wx1 * v01.x) + wy1 * (wx0 * v10.x + wx1 * v11.x);
-            const float ry = wy0 * (wx0 * v00.y + wx1 * v01.y) + wy1 * (wx0 * v10.y + wx1 * v11.y);
-            o[k] = pack2(rx, ry, is_fp16);
-        }
-        uint8_t* dst = out + ((((size_t)b * OH + oy) * OW + ox) * out_ld + out_choff + cv * 8) * 2;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int k = 0; k < 8; ++k) r[k] = wy0 * top[k] + wy1 * bot[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = top[k];
     }
+    uint8_t* dst = out + ((((size_t)b * OH + oy) * OW + ox) * out_ld + out_choff + cv * 8) * 2;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(r[0], r[1], F16), pack2(r[2], r[3], F16), pack2(r[4], r[5], F16), pack2(r[6], r[7], F16));
 }
 
 // ---------------------------------------------------------------------------------------------------------

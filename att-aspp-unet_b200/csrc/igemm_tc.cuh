@@ -21,6 +21,15 @@
 //                is one 32-pixel row of the tile; its 30 inner pixels are valid outputs, tiles overlap by two
 //                columns).  3x fewer MMAs and A loads -- what the small-N layers, which are limited by the
 //                shared-memory read of the A operand (64 cycles per MMA whatever N), need.
+//   AMODE_RS   : 3x3 / dilation 1 / small N with smem-resident weights.  ONE slab (KC, 32, TH+2) per channel chunk as in
+//                DXN, but the nine taps are nine MMAs that accumulate into the SAME columns: tap (dy, dx) reads the
+//                slab through an A descriptor whose start address is advanced by (dy*32 + dx) pixel rows.  The UMMA
+//                swizzle is a function of the absolute shared-memory address, so a start address that is not a
+//                multiple of the 8-row swizzle period reads exactly what TMA wrote (tools/mma_probe.cu, probe 2).
+//                Row r = ty*32 + j of the accumulator is output pixel (y0+ty, x0+j) for j < 30; j = 30, 31 wrap into
+//                the next slab row and are discarded.  Costs 3x the MMAs of DXN (each 32 + N/4 cycles: the shared-
+//                memory operand read, profiles/r01_mma_probe.txt) but needs no dx combination in the epilogue, which
+//                is what bounds the DXN layers whose K is small.
 //   With MT = 2 (SLAB, BN <= 128) a tile is two vertically adjacent 128-pixel blocks fed from one taller slab: every
 //   weight sub-block is used for two MMA groups, which halves the L2->SM weight traffic of the mid-size layers.
 // B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
@@ -51,7 +60,7 @@
 namespace aau {
 
 enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
-enum { AMODE_TAP = 0, AMODE_SLAB = 1, AMODE_DXN = 2 };
+enum { AMODE_TAP = 0, AMODE_SLAB = 1, AMODE_DXN = 2, AMODE_RS = 3 };
 enum { IGEMM_THREADS = 320, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12 };
 enum { ERR_PRODUCER_WAIT = 101, ERR_MMA_WAIT_FULL = 102, ERR_MMA_WAIT_TMEM = 103, ERR_EPI_WAIT = 104 };
 
@@ -103,6 +112,7 @@ struct alignas(64) IgemmParams {
     int VW;                 // valid output columns per tile (== TW except DXN: TW - 2)
     int nA, nB, b_resident; // ring depths; b_resident: nB == number of k-steps and B is loaded once
     int a_slot_bytes, b_slot_bytes, c_slot_bytes;
+    int cslots;             // staging tiles per epilogue group (2: a TMA store drains while the next tile is being staged)
     int pool, p_slot_bytes; // fused 2x2 max-pool of the stored tile (floor semantics), its staging slot size
     int b_region_bytes;     // nB * b_slot_bytes rounded up to 1024 (the staging tiles behind it need that alignment)
     int tmem_cols;
@@ -153,7 +163,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
     const int r = mt - tc.b * q.tiles_per_img;
     const int tyi = (int)fdiv((uint32_t)r, q.fd_tiles_x);
     tc.y0 = tyi * P.TH * P.MT;
-    tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode == AMODE_DXN ? 1 : 0);   // DXN: slab column 0 is the left halo
+    tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode >= AMODE_DXN ? 1 : 0);   // DXN / RS: slab column 0 is the left halo
     tc.n0 = nt * P.n_out;
     return tc;
 }
@@ -187,7 +197,7 @@ __device__ __forceinline__ void pool_staged_tile(const uint8_t* cs, uint8_t* ps,
 // field, so stepping K by 32 bytes is "+2" on the low word.
 template <int KK>
 __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                             uint32_t& accumulate) {
+                                             uint32_t accumulate) {
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
         const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
@@ -197,6 +207,12 @@ __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uin
     }
 }
 
+// The MMA role is executed by ALL 32 lanes of warp 1 with warp-uniform control flow (the warp index is broadcast
+// with a shuffle so that the compiler can prove it): every mbarrier wait is done by the whole warp and only the
+// tcgen05.mma / tcgen05.commit instructions sit under elect.sync.  Written as `if (threadIdx.x == 32)` the compiler
+// must assume divergence, wraps every UTCHMMA in an elect/branch "waterfall" loop and moves each descriptor from
+// vector to uniform registers first (R2UR): ~70-100 cycles per MMA instead of the 40-48 cycle hardware floor of
+// the small-N layers (profiles/r01_mma_probe.txt).
 template <int KK>
 __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a, uint64_t* empty_a,
                                          uint64_t* full_b, uint64_t* empty_b, uint64_t* b_res_bar, uint64_t* tmem_full_bar,
@@ -231,13 +247,33 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 const int bslot = res ? s : ib;
                 if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
-                mma_subblock<KK>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                ptx::umma_commit(&empty_a[ia]);
-                if (++ia == P.nA) { ia = 0; pa ^= 1; }
-                if (!res) {
-                    ptx::umma_commit(&empty_b[ib]);
-                    if (++ib == P.nB) { ib = 0; pb ^= 1; }
+                if (ptx::elect_one()) {
+                    mma_subblock<KK>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                    ptx::umma_commit(&empty_a[ia]);
+                    if (!res) ptx::umma_commit(&empty_b[ib]);
                 }
+                __syncwarp();
+                accumulate = 1;
+                if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                if (!res && ++ib == P.nB) { ib = 0; pb ^= 1; }
+            }
+        } else if (P.amode == AMODE_RS) {
+            const uint32_t row16 = (uint32_t)swz >> 4;                        // one pixel row of the slab, in 16-byte units
+            for (int ch = 0; ch < q.nchunk; ++ch) {
+                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t a_lo = a_base + ia * a_slot16;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {                       // B resident, TAP order: slot tap*nchunk + ch
+                        const uint32_t shift = (uint32_t)((tap / 3) * P.TW + (tap % 3)) * row16;
+                        mma_subblock<KK>(d_tmem, a_lo + shift, b_base + (uint32_t)(tap * q.nchunk + ch) * b_slot16, desc_hi, idesc, tap == 0 ? accumulate : 1u);
+                    }
+                    ptx::umma_commit(&empty_a[ia]);
+                }
+                __syncwarp();
+                accumulate = 1;
+                if (++ia == P.nA) { ia = 0; pa ^= 1; }
             }
         } else {
             int step = 0;
@@ -250,21 +286,24 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                     const int bslot = res ? step : ib;
                     if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
                     ptx::tc_fence_after();
-                    if (P.MT == 2) {                                          // second M-block: TH rows further down the slab
-                        uint32_t acc2 = accumulate;
-                        mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
+                    if (ptx::elect_one()) {
+                        if (P.MT == 2) {                                      // second M-block: TH rows further down the slab
+                            uint32_t acc2 = accumulate;
+                            mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
+                        }
+                        mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                        if (!res) ptx::umma_commit(&empty_b[ib]);
+                        if (dyi == 2) ptx::umma_commit(&empty_a[ia]);
                     }
-                    mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                    if (!res) {
-                        ptx::umma_commit(&empty_b[ib]);
-                        if (++ib == P.nB) { ib = 0; pb ^= 1; }
-                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (!res && ++ib == P.nB) { ib = 0; pb ^= 1; }
                 }
-                ptx::umma_commit(&empty_a[ia]);
                 if (++ia == P.nA) { ia = 0; pa ^= 1; }
             }
         }
-        ptx::umma_commit(&tmem_full_bar[acc]);                                // accumulator complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
 }
@@ -279,14 +318,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
     __shared__ __align__(16) float s_bias[2][2][256];       // [epilogue group][tile parity][channel]
     __shared__ __align__(16) float s_vec[256];
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and provably so for the compiler
     const int lane = threadIdx.x & 31;
     // operand tiles need 1024-byte alignment for the 128-byte swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + (size_t)P.nA * P.a_slot_bytes;
     uint8_t* smem_c = smem_b + (size_t)P.b_region_bytes;
-    uint8_t* smem_p = smem_c + 2 * (size_t)P.c_slot_bytes;
+    uint8_t* smem_p = smem_c + 2 * (size_t)P.cslots * P.c_slot_bytes;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.nprob; ++i) {
@@ -318,7 +357,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        // whole warp, warp-uniform control flow; the TMA instructions themselves are issued under elect.sync
+        {
             int ia = 0, ib = 0;
             uint32_t pa = 0, pb = 0;
             const bool res = P.b_resident != 0;
@@ -326,19 +366,22 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 const IgemmProblem& q = P.prob[0];
                 const int cin = q.nchunk * P.KC;
                 const int steps = (P.amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
-                ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
-                for (int s = 0; s < steps; ++s) {
-                    int kcoord = s * P.KC;                                    // TAP order: (tap, chunk)
-                    if (P.amode == AMODE_SLAB) {                              // SLAB order: (dx, chunk, dy)
-                        const int dyi = s % 3, dc = s / 3;
-                        const int dxi = dc / q.nchunk, ch = dc - dxi * q.nchunk;
-                        kcoord = (dyi * 3 + dxi) * cin + ch * P.KC;
-                    } else if (P.amode == AMODE_DXN) {                        // DXN order: (chunk, dy); K' = (dy, Cin)
-                        const int dyi = s % 3, ch = s / 3;
-                        kcoord = dyi * cin + ch * P.KC;
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
+                    for (int s = 0; s < steps; ++s) {
+                        int kcoord = s * P.KC;                                // TAP / RS order: (tap, chunk)
+                        if (P.amode == AMODE_SLAB) {                          // SLAB order: (dx, chunk, dy)
+                            const int dyi = s % 3, dc = s / 3;
+                            const int dxi = dc / q.nchunk, ch = dc - dxi * q.nchunk;
+                            kcoord = (dyi * 3 + dxi) * cin + ch * P.KC;
+                        } else if (P.amode == AMODE_DXN) {                    // DXN order: (chunk, dy); K' = (dy, Cin)
+                            const int dyi = s % 3, ch = s / 3;
+                            kcoord = dyi * cin + ch * P.KC;
+                        }
+                        ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)(blockIdx.x % q.n_tiles) * P.BN);
                     }
-                    ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)(blockIdx.x % q.n_tiles) * P.BN);
                 }
+                __syncwarp();
             }
             for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(P, t);
@@ -351,34 +394,44 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         int dy = 0, dx = 0;
                         if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
                         ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
-                        ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
-                        ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
-                        if (++ia == P.nA) { ia = 0; pa ^= 1; }
-                        if (!res) {
-                            ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
-                            ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
-                            ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC, tc.n0);
-                            if (++ib == P.nB) { ib = 0; pb ^= 1; }
+                        if (!res) ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
+                        if (ptx::elect_one()) {
+                            ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
+                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
+                            if (!res) {
+                                ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                                ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC, tc.n0);
+                            }
                         }
+                        __syncwarp();
+                        if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                        if (!res && ++ib == P.nB) { ib = 0; pb ^= 1; }
                     }
                 } else {
                     const int cin = q.nchunk * P.KC;
                     const uint32_t slab_bytes = (uint32_t)((P.TH * P.MT + 2) * P.TW * P.KC * 2);
                     const bool dxn = P.amode == AMODE_DXN;
-                    for (int dxi = 0; dxi < (dxn ? 1 : 3); ++dxi) {
+                    const bool one_slab = P.amode != AMODE_SLAB;              // DXN / RS: a single slab per channel chunk
+                    for (int dxi = 0; dxi < (one_slab ? 1 : 3); ++dxi) {
                         for (int ch = 0; ch < q.nchunk; ++ch) {
                             ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
-                            ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
-                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
-                                             dxn ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                            if (ptx::elect_one()) {
+                                ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
+                                ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
+                                                 one_slab ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                            }
+                            __syncwarp();
                             if (++ia == P.nA) { ia = 0; pa ^= 1; }
                             if (!res) {
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
-                                    ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
-                                    ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
-                                                     dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC,
-                                                     dxn ? (tc.n0 / P.n_out) * P.BN : tc.n0);
+                                    if (ptx::elect_one()) {
+                                        ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                                        ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
+                                                         dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC,
+                                                         dxn ? (tc.n0 / P.n_out) * P.BN : tc.n0);
+                                    }
+                                    __syncwarp();
                                     if (++ib == P.nB) { ib = 0; pb ^= 1; }
                                 }
                             }
@@ -389,7 +442,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        {
             if (P.KC == 64)      mma_role<4>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
             else if (P.KC == 32) mma_role<2>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
             else                 mma_role<1>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
@@ -412,8 +465,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         const int acc = grp;
         uint32_t acc_phase = 0;
         uint32_t c_phase = 0;
-        uint8_t* cs = smem_c + (size_t)grp * P.c_slot_bytes;    // this group's staging tile
-        uint8_t* ps = smem_p + (size_t)grp * P.p_slot_bytes;    // ... and pooled staging tile
+        int cslot = 0;                                          // this group's two staging tiles alternate per TMA store
+        uint8_t* cs = smem_c + (size_t)(grp * P.cslots) * P.c_slot_bytes;
+        uint8_t* ps = smem_p + (size_t)(grp * P.cslots) * P.p_slot_bytes;
+#define NEXT_CSLOT()                                                                   \
+    do {                                                                               \
+        cslot = (cslot + 1) & (P.cslots - 1);                                          \
+        cs = smem_c + (size_t)(grp * P.cslots + cslot) * P.c_slot_bytes;               \
+        ps = smem_p + (size_t)(grp * P.cslots + cslot) * P.p_slot_bytes;               \
+    } while (0)
+#define WAIT_STORE_READS()                                                             \
+    do {                                                                               \
+        if (P.cslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); \
+        else               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
+    } while (0)
         int par = 1;                                            // parity of this group's tile iteration
         uint64_t* cbar = &c_load_bar[grp];
         // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
@@ -425,8 +490,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         for (int t = blockIdx.x + grp * gridDim.x; t < P.total_tiles; t += 2 * gridDim.x) {
             const TileCoord tc = decode_tile(P, t);
             const IgemmProblem& q = P.prob[tc.pi];
-            const int y = tc.y0 + ty, x = tc.x0 + tx;
-            const bool valid = (y < q.H) && (x < q.W);
+            const int xoff = P.amode == AMODE_RS ? 1 : 0;           // RS: output column j sits at slab column j + 1
+            const int y = tc.y0 + ty, x = tc.x0 + xoff + tx;
+            const bool colok = P.amode != AMODE_RS || tx < P.VW;    // RS: the last two columns of a row are wrap-around garbage
+            const bool valid = (y < q.H) && (x < q.W) && colok;
+            const int srow = ty * P.VW + tx;                        // row inside the (CB, VW, TH) store box
             // bias of this tile, double-buffered by iteration parity (a slow thread may still read the previous one)
             par ^= 1;
             float* sb = s_bias[grp][par];
@@ -435,7 +503,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 for (int i = etid; i < P.n_out; i += 128)
                     sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout : tc.n0 + i));
             }
-            if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my previous stores have left smem
+            if (etid == 0) WAIT_STORE_READS();                  // the store that last used the next staging tile has left smem
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
             acc_phase ^= 1;
             ptx::tc_fence_after();
@@ -448,7 +516,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 const int N = P.n_out;
                 const bool inner = lane >= 1 && lane <= P.VW;                    // the 30 valid output columns
                 float dot = 0.f;
-                const int srow = quarter * P.VW + lane - 1;                      // row inside the (CB, VW, TH) store box
+                const int srow = quarter * P.VW + lane - 1;                      // DXN: output column = slab column - 1
                 for (int c0 = 0; c0 < N; c0 += 16) {
                     uint32_t e0[32], e1[32], e2[32];
                     ptx::tmem_ld_32x16(taddr + c0, e0);
@@ -509,6 +577,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                          ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    NEXT_CSLOT();
                 } else if (inner && valid) {
                     q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 }
@@ -517,8 +586,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 taddr = taddr0 + (uint32_t)(mb * P.BN);
                 const int yb = tc.y0 + mb * P.TH;
                 for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
-                    if (c0 > 0 || mb > 0) {                                     // reuse of the staging tile inside one accumulator
-                        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (c0 > 0 || mb > 0) {                                     // next staging tile: its store of two stores ago must be out
+                        if (etid == 0) WAIT_STORE_READS();
                         EPI_BAR();
                     }
                     for (int cc = 0; cc < P.CB; cc += 32) {
@@ -542,9 +611,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                     for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
                                 }
                                 const uint4 o = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
-                                uint32_t off = (uint32_t)(row * c_pitch + (cc + v * 8) * 2);
+                                uint32_t off = (uint32_t)(srow * c_pitch + (cc + v * 8) * 2);
                                 off ^= ((off >> 7) & swz_mask) << 4;          // TMA swizzle pattern of the staging tile
-                                *reinterpret_cast<uint4*>(cs + off) = o;
+                                if (colok) *reinterpret_cast<uint4*>(cs + off) = o;
                             }
                         }
                     }
@@ -556,7 +625,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
                     if (P.pool) {
-                        pool_staged_tile(cs, ps, P.TH, P.TW, c_pitch, swz_mask, etid, f16);
+                        pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                     }
@@ -567,12 +636,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
                         else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0), "r"(yb), "r"(tc.b) : "memory");
+                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
                         if (P.pool)
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"(tc.x0 >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
+                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    NEXT_CSLOT();
                 }
               }
             } else {
@@ -605,7 +675,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     // operand) -> multiply this thread's pixel row in shared memory -> TMA store, CB channels at a time
                     for (int c0 = 0; c0 < q.gate_C; c0 += P.CB) {
                         if (etid == 0) {
-                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            WAIT_STORE_READS();
                             ptx::mbar_expect_tx(cbar, (uint32_t)P.c_slot_bytes);
                             ptx::tma_load_4d(cs, &P.tmC[0], cbar, c0, tc.x0, tc.y0, tc.b);
                         }
@@ -629,11 +699,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                          ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
+                        NEXT_CSLOT();
                     }
                 }
             }
         }
 #undef EPI_BAR
+#undef NEXT_CSLOT
+#undef WAIT_STORE_READS
         if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores landed
     }
 

@@ -1,0 +1,200 @@
+// Micro-probes behind the igemm design decisions (results: profiles/r01_mma_probe.txt).
+//   1. cost of back-to-back tcgen05.mma (M=128, K=16) issued by one thread, as a function of N and of CTAs per SM
+//   2. A descriptors that start on a row that is not a multiple of 8 (base-offset field), needed for "row shift" taps
+//   3. tcgen05.ld throughput (TMEM -> registers) with 4 and 8 warps
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/mma_probe tools/mma_probe.cu
+#include "../att-aspp-unet_b200/csrc/ptx_sm100.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_bf16.h>
+
+using namespace aau;
+
+struct ProbeOut { long long issue, total; };
+
+// ---- 1. issue / completion cost of `reps` MMAs of width N
+// MODE 0: `if (threadIdx.x == 0)` single-thread role (divergent for the compiler: every UTCHMMA sits in a waterfall loop)
+// MODE 1: warp-uniform role (warp index broadcast with a shuffle), MMA / commit under elect.sync
+template <int MODE, int KC>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int reps, ProbeOut* out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar, bar2[8];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) ptx::mbar_init(&bar2[i], 1); ptx::fence_mbar_init(); }
+    if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_base_s, 256); ptx::tmem_relinquish(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform for the compiler
+    if (MODE == 1 ? (warp_u == 0) : (threadIdx.x == 0)) {
+        const uint32_t tm = tmem_base_s;
+        const uint32_t idesc = ptx::make_idesc_f16(128, N, false);
+        const uint64_t da = ptx::make_kmajor_desc(ptx::smem_u32(smem), 128);
+        const uint64_t db = ptx::make_kmajor_desc(ptx::smem_u32(smem + 16384), 128);
+        int nc = 0;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; r += 4) {
+            if (MODE == 0 || ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tm, da + 2 * k, db + 2 * k, idesc, (r | k) > 0);
+                if (KC) ptx::umma_commit(&bar2[nc & 7]);          // pipeline-style commit per 4-MMA sub-block (nobody waits)
+            }
+            if (MODE == 1) __syncwarp();
+            ++nc;
+        }
+        const long long t_issue = clock64() - t0;
+        if (MODE == 0 || ptx::elect_one()) ptx::umma_commit(&bar);
+        ptx::mbar_wait(&bar, 0, nullptr, 0);
+        const long long t1 = clock64() - t0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { out->issue = t_issue; out->total = t1; }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base_s, 256); }
+}
+
+// ---- 2. row-shifted A descriptor: D = A[row0 + r] . I  (B = 64x64 identity rows, N = 64, K = 64)
+__global__ void __launch_bounds__(128) rowshift_kernel(int row0, int use_base_offset, float* dout /* [128][64] */) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sa = smem;                   // 160 rows x 128 B, 128B-swizzled exactly as TMA would write them
+    uint8_t* sb = smem + 160 * 128;       // 64 rows x 128 B (1024-aligned: 160*128 = 20480)
+    for (int i = threadIdx.x; i < 160 * 64; i += blockDim.x) {
+        const int r = i / 64, k = i % 64;
+        const float v = (float)(r * 2 + (k == (r % 64) ? 1 : 0));       // A[r][k] = 2r (+1 on a diagonal): exact in bf16 for r < 128
+        uint32_t off = (uint32_t)(r * 128 + k * 2);
+        off ^= ((off >> 7) & 7) << 4;
+        *reinterpret_cast<__nv_bfloat16*>(sa + off) = __float2bfloat16(v);
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int n = i / 64, k = i % 64;
+        uint32_t off = (uint32_t)(n * 128 + k * 2);
+        off ^= ((off >> 7) & 7) << 4;
+        *reinterpret_cast<__nv_bfloat16*>(sb + off) = __float2bfloat16(n == k ? 1.f : 0.f);
+    }
+    if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
+    if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_base_s, 64); ptx::tmem_relinquish(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tm = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = ptx::make_idesc_f16(128, 64, false);
+        const uint32_t a_addr = ptx::smem_u32(sa) + (uint32_t)row0 * 128u;
+        uint64_t da = ptx::make_kmajor_desc(a_addr, 128);
+        if (use_base_offset) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
+        const uint64_t db = ptx::make_kmajor_desc(ptx::smem_u32(sb), 128);
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tm, da + 2 * k, db + 2 * k, idesc, k > 0);
+        ptx::umma_commit(&bar);
+    }
+    ptx::mbar_wait(&bar, 0, nullptr, 0);
+    ptx::tc_fence_after();
+    const int warp = threadIdx.x >> 5;
+    uint32_t r[32];
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        ptx::tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16) + c0, r);
+        ptx::tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) dout[threadIdx.x * 64 + c0 + i] = __uint_as_float(r[i]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tm, 64); }
+}
+
+// ---- 3. tcgen05.ld throughput: every warp reads its lane quarter, `cols` columns, `reps` times
+__global__ void __launch_bounds__(256) tmem_ld_kernel(int cols, int reps, ProbeOut* out, float* sink) {
+    __shared__ uint32_t tmem_base_s;
+    if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_base_s, 256); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tm = tmem_base_s + ((uint32_t)((threadIdx.x >> 5) & 3) * 32 << 16);
+    float acc = 0.f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+        for (int c = 0; c < cols; c += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(tm + c, v);
+            ptx::tmem_ld_wait();
+            acc += __uint_as_float(v[0]) + __uint_as_float(v[31]);
+        }
+    __syncthreads();
+    const long long t1 = clock64() - t0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out->issue = t1; out->total = t1; }
+    if (acc == 12345.f) sink[threadIdx.x] = acc;
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base_s, 256); }
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+int main() {
+    ProbeOut* d;
+    CK(cudaMalloc(&d, sizeof(ProbeOut)));
+    float* sink;
+    CK(cudaMalloc(&sink, 4096));
+    CK(cudaFuncSetAttribute(rowshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    const int reps = 512;
+    printf("# 1. back-to-back tcgen05.mma M=128 K=16, %d MMAs in groups of 4; cycles per MMA (issue loop / until the final commit arrives)\n", reps);
+    auto run1 = [&](auto kern, const char* what) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        for (int ctas : {1, 2})
+            for (int N : {16, 32, 64, 96, 128, 256}) {
+                ProbeOut h;
+                for (int it = 0; it < 2; ++it) {
+                    kern<<<148 * ctas, 128, 52 * 1024>>>(N, reps, d);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+                printf("%s ctas/SM %d N=%3d : issue %.1f  total %.1f  (nominal N/2 = %d)\n", what, ctas, N, (double)h.issue / reps, (double)h.total / reps, N / 2);
+            }
+    };
+    run1(mma_rate_kernel<0, 0>, "if(thread==0), no commits      ");
+    run1(mma_rate_kernel<0, 1>, "if(thread==0), commit per 4    ");
+    run1(mma_rate_kernel<1, 0>, "warp-uniform+elect, no commits ");
+    run1(mma_rate_kernel<1, 1>, "warp-uniform+elect, commit per 4");
+    printf("# 2. row-shifted A descriptor (start row not a multiple of 8)\n");
+    float* dout;
+    CK(cudaMalloc(&dout, 128 * 64 * 4));
+    std::vector<float> ho(128 * 64);
+    for (int row0 : {0, 1, 3, 8, 9}) {
+        for (int ubo : {0, 1}) {
+            rowshift_kernel<<<1, 128, 64 * 1024>>>(row0, ubo, dout);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("row0 %d base_offset %d: CUDA error %s\n", row0, ubo, cudaGetErrorString(e)); return 0; }
+            CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
+            int bad = 0;
+            for (int r = 0; r < 128; ++r)
+                for (int k = 0; k < 64; ++k) {
+                    const int ar = r + row0;
+                    const float want = (float)(ar * 2 + (k == (ar % 64) ? 1 : 0));
+                    if (ho[r * 64 + k] != want) ++bad;
+                }
+            printf("row0 %d base_offset_field %d : %d wrong of 8192 (D[0][0..2] = %g %g %g, D[1][0..2] = %g %g %g)\n", row0, ubo, bad, ho[0], ho[1], ho[2], ho[64], ho[65], ho[66]);
+        }
+    }
+    printf("# 3. tcgen05.ld 32x32b.x32 throughput, one CTA per SM\n");
+    for (int threads : {128, 256}) {
+        for (int cols : {32, 96, 256}) {
+            ProbeOut h;
+            const int r2 = 64;
+            for (int it = 0; it < 2; ++it) {
+                tmem_ld_kernel<<<148, threads>>>(cols, r2, d, sink);
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+            const double bytes = (double)r2 * cols * 4 * threads;
+            printf("threads %d cols %3d : %.1f cycles per pass, %.1f B/clk/SM\n", threads, cols, (double)h.total / r2, bytes / (double)h.total);
+        }
+    }
+    return 0;
+}
