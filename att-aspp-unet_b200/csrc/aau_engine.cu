@@ -121,6 +121,8 @@ struct Engine {
     int opt_mt = 2;
     int opt_cslots = 0;
     int opt_rs = 1;
+    int opt_titer = 1;
+    int opt_ng = 0;                                   // 0: planner's choice, 2 / 4: force the number of epilogue groups
     int opt_ctas = 0;
     int opt_profile = 0;
     Plan* last_plan = nullptr;
@@ -581,50 +583,65 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.pool = want_pool ? 1 : 0;
     P.p_slot_bytes = want_pool ? ((((P.TH / 2) * (P.VW / 2) * P.CB * 2) + 1023) & ~1023) : 0;
     int c_bytes = 0;                                              // staging tiles: cslots per epilogue group, chosen below
-    P.acc_stages = 2;                                             // epilogue group g drains stage g
-    P.tmem_cols = 32;
-    while (P.tmem_cols < P.acc_stages * BN * P.MT) P.tmem_cols <<= 1;
-    // CTAs per SM: small-N layers are limited by the single MMA-issuing thread and by the epilogue, not by the
-    // tensor pipe, so several CTAs share an SM there (TMEM: 512 columns per SM, registers: 3 x 192 threads fit).
+    // CTAs per SM: small-N layers are paced by the per-tile epilogue latency chain, not by the tensor pipe, so two CTAs
+    // share an SM there when shared memory allows it (each with 2 accumulator stages / epilogue groups).  When only one
+    // CTA fits and four accumulators fit in the 512 TMEM columns, that CTA runs 4 stages / groups instead.
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
     // n_tiles so that the static striding keeps every CTA on the same N tile
     const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn) && e.opt_resident != 0;
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
-    int ctas = (BN <= 128 || P.acc_stages == 1) ? 2 : 1;          // measured: 2 CTAs co-reside, a third only queues
-    ctas = std::min(ctas, 512 / P.tmem_cols);
-    if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / P.tmem_cols);   // negative: force, skip the occupancy clamp
+    auto cols_for = [&](int stages) { int c = 32; while (c < stages * BN * P.MT) c <<= 1; return c; };
+    int ctas = (BN <= 128) ? 2 : 1;                               // measured: 2 CTAs co-reside, a third only queues
+    ctas = std::min(ctas, 512 / cols_for(2));
+    if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / cols_for(2));
+    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE;
     bool ok = false;
+    int ng = 2;
     for (; ctas >= 1 && !ok; --ctas) {
         const int budget = std::min(233472 / ctas - 7168, 232448 - 6144) - 1024;   // static smem + 1 KB driver reserve + alignment slack
-        // pass 0/1: weights resident, two / one staging tiles per epilogue group; pass 2/3: weights streamed, two / one
-        for (int pass = 0; pass < 4 && !ok; ++pass) {
-            const bool res = pass < 2 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
-            if (pass < 2 && !res) continue;
-            if (rs && !res) continue;                              // row-shifted taps index the resident weight matrix
-            const int cslots = (pass & 1) ? 1 : 2;
-            if (cslots == 2 && (!tma_out || e.opt_cslots == 1)) continue;
-            c_bytes = tma_out ? 2 * cslots * (P.c_slot_bytes + P.p_slot_bytes) : 0;
-            P.cslots = cslots;
-            const int fixed = c_bytes + (res ? res_bytes : 0);
-            const int unit = res ? P.a_slot_bytes : (slab ? P.a_slot_bytes + 3 * P.b_slot_bytes : P.a_slot_bytes + P.b_slot_bytes);
-            int n = (budget - fixed) / unit;
-            int nb = n * (slab ? 3 : 1);
-            if (n < 2 && !res && slab) {                           // tight fit: two slabs and whatever B slots remain (>= 4)
-                nb = (budget - fixed - 2 * P.a_slot_bytes) / P.b_slot_bytes;
-                n = nb >= 4 ? 2 : 0;
+        for (int gsel = 0; gsel < 2 && !ok; ++gsel) {
+            ng = (gsel == 0) ? 4 : 2;
+            if (ng == 4 && !(ng4_ok && (ctas == 1 || e.opt_ng == 4))) continue;
+            if (ng == 4 && ctas * cols_for(4) > 512) continue;
+            // passes 0-2: weights resident with (all chunks of a tile | two | one) staging tiles per epilogue group;
+            // passes 3-5: the same with streamed weights
+            const int nchunks = (P.amode == AMODE_DXN) ? 1 : P.MT * BN / P.CB;
+            for (int pass = 0; pass < 6 && !ok; ++pass) {
+                const bool res = pass < 3 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
+                if (pass < 3 && !res) continue;
+                if (rs && !res) continue;                          // row-shifted taps index the resident weight matrix
+                const int sel = pass % 3;
+                const bool cbatch = sel == 0;
+                if (cbatch && !((d0.epi == EPI_STORE || d0.epi == EPI_CONVT) && nchunks >= 2 && nchunks <= 4 && e.opt_cslots == 0)) continue;
+                const int cslots = cbatch ? nchunks : (sel == 1 ? 2 : 1);
+                if (sel == 1 && (!tma_out || e.opt_cslots == 1)) continue;
+                P.cbatch = cbatch ? 1 : 0;
+                c_bytes = tma_out ? ng * cslots * (P.c_slot_bytes + P.p_slot_bytes) : 0;
+                P.cslots = cslots;
+                const int fixed = c_bytes + (res ? res_bytes : 0);
+                const int unit = res ? P.a_slot_bytes : (slab ? P.a_slot_bytes + 3 * P.b_slot_bytes : P.a_slot_bytes + P.b_slot_bytes);
+                int n = (budget - fixed) / unit;
+                int nb = n * (slab ? 3 : 1);
+                if (n < 2 && !res && slab) {                       // tight fit: two slabs and whatever B slots remain (>= 4)
+                    nb = (budget - fixed - 2 * P.a_slot_bytes) / P.b_slot_bytes;
+                    n = nb >= 4 ? 2 : 0;
+                }
+                if (n < (cslots >= 2 ? 3 : 2)) continue;           // extra staging tiles must not starve the operand rings
+                P.b_resident = res ? 1 : 0;
+                P.nA = std::min((int)IGEMM_MAX_SLOTS, n);
+                P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, nb);
+                ok = true;
             }
-            if (n < (cslots == 2 ? 3 : 2)) continue;               // a second staging tile must not starve the operand rings
-            P.b_resident = res ? 1 : 0;
-            P.nA = std::min((int)IGEMM_MAX_SLOTS, n);
-            P.nB = res ? steps : std::min((int)IGEMM_MAX_SLOTS, nb);
-            ok = true;
         }
         if (ok) break;
     }
     if (!ok) return e.fail(AAU_ERR_INVALID, "pipeline does not fit in shared memory");
+    P.acc_stages = ng;                                            // epilogue group g drains accumulator stage g
+    P.tmem_cols = cols_for(ng);
     const int b_region = ((P.nB * P.b_slot_bytes) + 1023) & ~1023;
     P.b_region_bytes = b_region;
     P.is_fp16 = e.is_fp16() ? 1 : 0;
+    P.tile_iter = e.opt_titer;
     P.err = e.d_err;
     P.nprob = (int)descs.size();
     int tile_begin = 0;
@@ -719,15 +736,22 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     int grid = std::min(P.total_tiles, e.num_sms * ctas);
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
     oi.name += " [" + std::string(rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap"))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
-               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots == 2 ? " c2" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
-    plan.ops.push_back([P, grid, smem, patch_aux](const FwdArgs& a) -> cudaError_t {
+    const bool f16k = e.is_fp16();
+    plan.ops.push_back([P, grid, smem, patch_aux, ng, f16k](const FwdArgs& a) -> cudaError_t {
         IgemmParams Q = P;
         if (patch_aux == 1) Q.prob[0].aux = a.logits;
         if (patch_aux == 2) Q.prob[0].aux = a.psi3;
         if (patch_aux == 3) Q.prob[0].aux = a.psi2;
-        igemm_tc_kernel<<<grid, IGEMM_THREADS, smem, a.stream>>>(Q);
+        if (ng == 4) {
+            if (f16k) igemm_tc_kernel<4, true><<<grid, igemm_threads(4), smem, a.stream>>>(Q);
+            else      igemm_tc_kernel<4, false><<<grid, igemm_threads(4), smem, a.stream>>>(Q);
+        } else {
+            if (f16k) igemm_tc_kernel<2, true><<<grid, igemm_threads(2), smem, a.stream>>>(Q);
+            else      igemm_tc_kernel<2, false><<<grid, igemm_threads(2), smem, a.stream>>>(Q);
+        }
         return cudaGetLastError();
     });
     return AAU_OK;
@@ -908,7 +932,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         if (fix) {
             const View in = tmpg[l];
             const long long items = (long long)B * Hs[l] * Ws[l] * (ch[l] / 8);
-            const dim3 grid((unsigned)((Ws[l] * (ch[l] / 8) + 255) / 256), (unsigned)Hs[l], (unsigned)B);
+            const dim3 grid((unsigned)((Ws[l] * (ch[l] / 8) + 255) / 256), (unsigned)((Hs[l] + RESIZE_ROWS - 1) / RESIZE_ROWS), (unsigned)B);
             OpInfo oi;
             oi.name = p + ".up bilinear fix-up";
             oi.kernel = "resize_bilinear_kernel";
@@ -994,8 +1018,12 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         delete h;
         return AAU_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144) != cudaSuccess ||
-        cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+    auto raise_smem = [](const void* fn) {
+        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144) == cudaSuccess &&
+               cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    };
+    if (!raise_smem((const void*)igemm_tc_kernel<2, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true>) ||
+        !raise_smem((const void*)igemm_tc_kernel<4, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true>)) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;
@@ -1223,8 +1251,8 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         h->e.last_plan = nullptr;
         return AAU_OK;
     }
-    if (std::string(name) == "rs") {
-        h->e.opt_rs = value;
+    if (std::string(name) == "rs" || std::string(name) == "ng" || std::string(name) == "titer") {
+        (std::string(name) == "rs" ? h->e.opt_rs : (std::string(name) == "ng" ? h->e.opt_ng : h->e.opt_titer)) = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

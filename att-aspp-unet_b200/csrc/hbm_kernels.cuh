@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(512) aspp_pool_bias_kernel(const float* __rest
 // floor-pooled skip is one row/column larger than the transposed-conv output
 // (attention_aspp_unet_pipeline_stage.py:106-107).  Index arithmetic follows ATen's upsample_bilinear2d:
 // scale = in/out, src = max(0, scale*(dst+0.5)-0.5), i0 = floor(src), i1 = min(i0+1, in-1), w1 = src-i0.
-// grid = (ceil(OW*C/8 / 256), OH, B): a thread produces 8 channels of one output pixel (16-byte vector).  An axis
+// grid = (ceil(OW*C/8 / 256), ceil(OH / RESIZE_ROWS), B): a thread produces 8 channels (one 16-byte vector) of one output column.  An axis
 // whose size does not change has scale 1, so its second sample has weight exactly 0 and is neither read nor blended
 // (v*1 + u*0 == v for finite u): the usual one-axis fix-up is two reads (adjacent rows or pixels: L2 hits), eight
 // 2-term blends and one write per thread.  Instantiated per storage type so that unpack / pack are two instructions.
@@ -212,6 +212,10 @@ __device__ __forceinline__ void blend8(const uint4& p, const uint4& q, float wp,
         o[2 * k + 1] = wp * u.y + wq * v.y;
     }
 }
+// A thread walks RESIZE_ROWS consecutive output rows of its (column, 8-channel) slot and keeps the lower source row
+// of one output row as the upper source row of the next when they coincide (they do whenever the scale is ~1), so
+// the one-row fix-up reads every input row once.
+enum { RESIZE_ROWS = 8 };
 template <bool F16>
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __restrict__ in, int IH, int IW, int C,
                                                               uint8_t* __restrict__ out, int OH, int OW, int out_ld, int out_choff,
@@ -220,31 +224,49 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __r
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= OW * CV) return;
     const int ox = i / CV, cv = i - ox * CV;
-    const int oy = blockIdx.y, b = blockIdx.z;
+    const int oy0 = blockIdx.y * RESIZE_ROWS, b = blockIdx.z;
     const float sh = (float)IH / (float)OH, sw = (float)IW / (float)OW;
-    const float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = min(y0 + 1, IH - 1), x1 = min(x0 + 1, IW - 1);
-    const float wy1 = fy - (float)y0, wx1 = fx - (float)x0;
-    const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    const float fx = fmaxf(sw * ((float)ox + 0.5f) - 0.5f, 0.f);
+    const int x0 = (int)fx, x1 = min(x0 + 1, IW - 1);
+    const float wx1 = fx - (float)x0, wx0 = 1.f - wx1;
+    const bool two_x = IW != OW, two_y = IH != OH;
     const uint8_t* base = in + (size_t)b * IH * IW * C * 2 + (size_t)cv * 16;
-    const uint4 q00 = __ldg((const uint4*)(base + ((size_t)y0 * IW + x0) * C * 2));
-    float top[8], r[8];
-    if (IW != OW) blend8<F16>(q00, __ldg((const uint4*)(base + ((size_t)y0 * IW + x1) * C * 2)), wx0, wx1, top);
-    else          blend8<F16>(q00, q00, 1.f, 0.f, top);
-    if (IH != OH) {
-        const uint4 q10 = __ldg((const uint4*)(base + ((size_t)y1 * IW + x0) * C * 2));
-        float bot[8];
-        if (IW != OW) blend8<F16>(q10, __ldg((const uint4*)(base + ((size_t)y1 * IW + x1) * C * 2)), wx0, wx1, bot);
-        else          blend8<F16>(q10, q10, 1.f, 0.f, bot);
+    auto load_row = [&](int y, float (&r)[8]) {                   // horizontally blended source row y at this output column
+        const uint4 q0 = __ldg((const uint4*)(base + ((size_t)y * IW + x0) * C * 2));
+        if (two_x) blend8<F16>(q0, __ldg((const uint4*)(base + ((size_t)y * IW + x1) * C * 2)), wx0, wx1, r);
+        else       blend8<F16>(q0, q0, 1.f, 0.f, r);
+    };
+    float top[8], bot[8];
+    int have_top = -1, have_bot = -1;                             // source rows currently held
+    uint8_t* dst = out + ((((size_t)b * OH + oy0) * OW + ox) * out_ld + out_choff + cv * 8) * 2;
+    const size_t row_bytes = (size_t)OW * out_ld * 2;
+#pragma unroll 1
+    for (int k = 0; k < RESIZE_ROWS; ++k, dst += row_bytes) {
+        const int oy = oy0 + k;
+        if (oy >= OH) break;
+        const float fy = fmaxf(sh * ((float)oy + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)fy, y1 = min(y0 + 1, IH - 1);
+        const float wy1 = fy - (float)y0, wy0 = 1.f - wy1;
+        if (y0 != have_top) {
+            if (y0 == have_bot) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = wy0 * top[k] + wy1 * bot[k];
-    } else {
+                for (int j = 0; j < 8; ++j) top[j] = bot[j];
+            } else {
+                load_row(y0, top);
+            }
+            have_top = y0;
+        }
+        float r[8];
+        if (two_y) {
+            if (y1 != have_bot) { load_row(y1, bot); have_bot = y1; }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = top[k];
+            for (int j = 0; j < 8; ++j) r[j] = wy0 * top[j] + wy1 * bot[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = top[j];
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(r[0], r[1], F16), pack2(r[2], r[3], F16), pack2(r[4], r[5], F16), pack2(r[6], r[7], F16));
     }
-    uint8_t* dst = out + ((((size_t)b * OH + oy) * OW + ox) * out_ld + out_choff + cv * 8) * 2;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(r[0], r[1], F16), pack2(r[2], r[3], F16), pack2(r[4], r[5], F16), pack2(r[6], r[7], F16));
 }
 
 // ---------------------------------------------------------------------------------------------------------

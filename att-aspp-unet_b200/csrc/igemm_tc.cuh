@@ -61,7 +61,8 @@ namespace aau {
 
 enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
 enum { AMODE_TAP = 0, AMODE_SLAB = 1, AMODE_DXN = 2, AMODE_RS = 3 };
-enum { IGEMM_THREADS = 320, IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12 };
+enum { IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12, IGEMM_MAX_GROUPS = 4 };
+__host__ __device__ constexpr int igemm_threads(int ng) { return 64 + 128 * ng; }   // TMA warp + MMA warp + ng epilogue groups of 4 warps
 enum { ERR_PRODUCER_WAIT = 101, ERR_MMA_WAIT_FULL = 102, ERR_MMA_WAIT_TMEM = 103, ERR_EPI_WAIT = 104 };
 
 // Division by a launch-time constant as multiply-high + shift (the tile decode runs once per tile per role and four
@@ -113,11 +114,13 @@ struct alignas(64) IgemmParams {
     int nA, nB, b_resident; // ring depths; b_resident: nB == number of k-steps and B is loaded once
     int a_slot_bytes, b_slot_bytes, c_slot_bytes;
     int cslots;             // staging tiles per epilogue group (2: a TMA store drains while the next tile is being staged)
+    int cbatch;             // cslots == chunks per tile: stage the whole tile, then one fence / barrier / store group
     int pool, p_slot_bytes; // fused 2x2 max-pool of the stored tile (floor semantics), its staging slot size
     int b_region_bytes;     // nB * b_slot_bytes rounded up to 1024 (the staging tiles behind it need that alignment)
     int tmem_cols;
     int acc_stages;         // TMEM accumulator stages (2, or 1 when 2*BN columns would leave no room for a second CTA)
     int is_fp16;
+    int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int* err;
 };
 
@@ -129,6 +132,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_fp16) {
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+// round-to-nearest pack with the ReLU clamp folded into the conversion instruction (cvt.rn.relu.*x2.f32)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t r;
+    if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ float2 unpack2(uint32_t v, int is_fp16) {
     if (is_fp16) return __half22float2(*reinterpret_cast<__half2*>(&v));
@@ -145,6 +156,16 @@ __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_fp16) {
 }
 __device__ __forceinline__ uint4 max8(uint4 a, uint4 b, int f) {
     return make_uint4(max2(a.x, b.x, f), max2(a.y, b.y, f), max2(a.z, b.z, f), max2(a.w, b.w, f));
+}
+// 16-byte shared-memory accesses through 32-bit shared addresses (a generic pointer costs 64-bit address arithmetic
+// and a generic ST/LD per access in the epilogue's innermost loops)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 struct TileCoord { int pi, b, y0, x0, n0; };
 
@@ -169,28 +190,83 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
 }
 
 
+// Tile walk of one role: t = first, first + stride, ...  For single-problem launches the (n tile, x, y, frame)
+// coordinates advance by the stride's own mixed-radix digits with carries (a handful of adds per tile); the three
+// divisions are done once.  The roles are single warps running serial instruction streams, and for the small-K
+// layers a full decode per tile was a visible share of the MMA warp's time per tile.
+struct TileIter {
+    int t, stride, total;
+    int nt, x, y, b;          // current digits
+    int s_nt, s_x, s_y, s_b;  // digits of the stride
+    int tiles_x, tiles_y, n_tiles;
+    bool incremental;
+    __device__ __forceinline__ void init(const IgemmParams& P, int first, int stride_) {
+        t = first; stride = stride_; total = P.total_tiles;
+        incremental = P.nprob == 1 && P.tile_iter != 0;
+        if (incremental) {
+            const IgemmProblem& q = P.prob[0];
+            tiles_x = q.tiles_x; n_tiles = q.n_tiles;
+            tiles_y = (int)fdiv((uint32_t)q.tiles_per_img, q.fd_tiles_x);
+            auto digits = [&](int v, int& dn, int& dx, int& dy, int& db) {
+                const int m = (int)fdiv((uint32_t)v, q.fd_n_tiles);
+                dn = v - m * q.n_tiles;
+                db = (int)fdiv((uint32_t)m, q.fd_tiles_per_img);
+                const int r = m - db * q.tiles_per_img;
+                dy = (int)fdiv((uint32_t)r, q.fd_tiles_x);
+                dx = r - dy * q.tiles_x;
+            };
+            digits(first, nt, x, y, b);
+            digits(stride_, s_nt, s_x, s_y, s_b);
+        }
+    }
+    __device__ __forceinline__ bool valid() const { return t < total; }
+    __device__ __forceinline__ void next() {
+        t += stride;
+        if (incremental) {
+            nt += s_nt;
+            int c = nt >= n_tiles ? 1 : 0;
+            nt -= c ? n_tiles : 0;
+            x += s_x + c;
+            c = x >= tiles_x ? 1 : 0;
+            x -= c ? tiles_x : 0;
+            y += s_y + c;
+            c = y >= tiles_y ? 1 : 0;
+            y -= c ? tiles_y : 0;
+            b += s_b + c;
+        }
+    }
+    __device__ __forceinline__ TileCoord coord(const IgemmParams& P) const {
+        if (!incremental) return decode_tile(P, t);
+        TileCoord tc;
+        tc.pi = 0;
+        tc.b = b;
+        tc.y0 = y * P.TH * P.MT;
+        tc.x0 = x * P.VW - (P.amode >= AMODE_DXN ? 1 : 0);
+        tc.n0 = nt * P.n_out;
+        return tc;
+    }
+};
+
 // MaxPool2d(2) of a staged output tile (rows = th x vw pixels, c_pitch bytes each, TMA-swizzled) into a staged
-// pooled tile ((th/2) x (vw/2) pixels, same pitch / swizzle).  One 16-byte vector (8 channels) per thread-iteration.
-__device__ __forceinline__ void pool_staged_tile(const uint8_t* cs, uint8_t* ps, int th, int vw, int c_pitch, uint32_t swz_mask,
+// pooled tile ((th/2) x (vw/2) pixels, same pitch / swizzle).  One 16-byte vector (8 channels) per thread-iteration;
+// c_pitch / 16 is a power of two, so a thread keeps its vector index and walks pooled pixels (no divisions).
+__device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int th, int vw, int c_pitch, uint32_t swz_mask,
                                                  int etid, int f16) {
-    const int PW = vw >> 1, PH = th >> 1, cv = c_pitch >> 4;
-    for (int it = etid; it < PW * PH * cv; it += 128) {           // 128 threads per epilogue group
-        const int v = it % cv, pp = it / cv;
-        const int py = pp / PW, px = pp - py * PW;
-        const int r00 = (2 * py) * vw + 2 * px;
-        uint4 m;
-        {
+    const int PW = vw >> 1, PH = th >> 1;
+    const int lcv = 31 - __clz(c_pitch >> 4);                     // log2(vectors per pixel): 1, 2 or 3
+    const int v = etid & ((1 << lcv) - 1), px0 = etid >> lcv, pstep = 128 >> lcv;   // 128 threads per epilogue group
+    for (int py = 0; py < PH; ++py)
+        for (int px = px0; px < PW; px += pstep) {
+            const int r00 = (2 * py) * vw + 2 * px;
             uint32_t o0 = (uint32_t)(r00 * c_pitch + v * 16), o1 = o0 + (uint32_t)c_pitch;
             uint32_t o2 = o0 + (uint32_t)(vw * c_pitch), o3 = o2 + (uint32_t)c_pitch;
             o0 ^= ((o0 >> 7) & swz_mask) << 4; o1 ^= ((o1 >> 7) & swz_mask) << 4;
             o2 ^= ((o2 >> 7) & swz_mask) << 4; o3 ^= ((o3 >> 7) & swz_mask) << 4;
-            m = max8(max8(*reinterpret_cast<const uint4*>(cs + o0), *reinterpret_cast<const uint4*>(cs + o1), f16),
-                     max8(*reinterpret_cast<const uint4*>(cs + o2), *reinterpret_cast<const uint4*>(cs + o3), f16), f16);
+            const uint4 m = max8(max8(lds128(cs + o0), lds128(cs + o1), f16), max8(lds128(cs + o2), lds128(cs + o3), f16), f16);
+            uint32_t po = (uint32_t)((py * PW + px) * c_pitch + v * 16);
+            po ^= ((po >> 7) & swz_mask) << 4;
+            sts128(ps + po, m);
         }
-        uint32_t po = (uint32_t)(pp * c_pitch + v * 16);
-        po ^= ((po >> 7) & swz_mask) << 4;
-        *reinterpret_cast<uint4*>(ps + po) = m;
-    }
 }
 
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
@@ -233,8 +309,9 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     uint32_t acc_phase = 0;
     const bool res = P.b_resident != 0;
     if (res) ptx::mbar_wait(b_res_bar, 0, P.err, ERR_MMA_WAIT_FULL);
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(P, t);
+    TileIter it;
+    for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
+        const TileCoord tc = it.coord(P);
         const IgemmProblem& q = P.prob[tc.pi];
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
         ptx::tc_fence_after();
@@ -308,14 +385,17 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     }
 }
 
-__global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
+// NG = epilogue groups = TMEM accumulator stages (2, or 4 for single-CTA-per-SM layers whose 4 accumulators fit in
+// the 512 TMEM columns: there the per-tile epilogue latency chain, not the tensor pipe, sets the pace).
+template <int NG, bool F16>
+__global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
     __shared__ __align__(8) uint64_t full_b[IGEMM_MAX_SLOTS], empty_b[IGEMM_MAX_SLOTS];
-    __shared__ __align__(8) uint64_t b_res_bar, c_load_bar[2];
-    __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t b_res_bar, c_load_bar[NG];
+    __shared__ __align__(8) uint64_t tmem_full_bar[NG], tmem_empty_bar[NG];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float s_bias[2][2][256];       // [epilogue group][tile parity][channel]
+    __shared__ __align__(16) float s_bias[1024];            // [epilogue group][tile parity][512 / NG channels]
     __shared__ __align__(16) float s_vec[256];
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and provably so for the compiler
@@ -325,7 +405,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + (size_t)P.nA * P.a_slot_bytes;
     uint8_t* smem_c = smem_b + (size_t)P.b_region_bytes;
-    uint8_t* smem_p = smem_c + 2 * (size_t)P.cslots * P.c_slot_bytes;
+    uint8_t* smem_p = smem_c + (size_t)(NG * P.cslots) * P.c_slot_bytes;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < P.nprob; ++i) {
@@ -336,9 +416,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         if (!P.b_resident)
             for (int s = 0; s < P.nB; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
         ptx::mbar_init(&b_res_bar, 1);
-        ptx::mbar_init(&c_load_bar[0], 1);
-        ptx::mbar_init(&c_load_bar[1], 1);
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NG; ++a) {
+            ptx::mbar_init(&c_load_bar[a], 1);
             ptx::mbar_init(&tmem_full_bar[a], 1);
             ptx::mbar_init(&tmem_empty_bar[a], 4);     // one arrive per epilogue warp of the owning group
         }
@@ -349,7 +428,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         ptx::tmem_relinquish();
     }
     if (threadIdx.x >= 64 && P.prob[0].vec != nullptr)                        // GATE / OUTCONV vector, constant per launch
-        for (int i = threadIdx.x - 64; i < P.n_out; i += 256) s_vec[i] = P.prob[0].vec[i];
+        for (int i = threadIdx.x - 64; i < P.n_out; i += 128 * NG) s_vec[i] = P.prob[0].vec[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -383,8 +462,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                 }
                 __syncwarp();
             }
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(P, t);
+            TileIter it;
+            for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
+                const TileCoord tc = it.coord(P);
                 const IgemmProblem& q = P.prob[tc.pi];
                 if (P.amode == AMODE_TAP) {
                     const int steps = q.taps * q.nchunk;
@@ -459,7 +539,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         const int etid = (threadIdx.x - 64) & 127;              // 0..127 inside the group
         const int ty = row >> P.tw_shift;
         const int tx = row & (P.TW - 1);
-        const int f16 = P.is_fp16;
+        constexpr int f16 = F16 ? 1 : 0;
         const int c_pitch = P.CB * 2;                           // bytes per staged row == store swizzle width
         const uint32_t swz_mask = (uint32_t)(c_pitch >> 4) - 1; // 7 / 3 / 1 for 128 / 64 / 32-byte swizzle
         const int acc = grp;
@@ -470,25 +550,39 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
         uint8_t* ps = smem_p + (size_t)(grp * P.cslots) * P.p_slot_bytes;
 #define NEXT_CSLOT()                                                                   \
     do {                                                                               \
-        cslot = (cslot + 1) & (P.cslots - 1);                                          \
+        cslot = (cslot + 1 == P.cslots) ? 0 : cslot + 1;                               \
         cs = smem_c + (size_t)(grp * P.cslots + cslot) * P.c_slot_bytes;               \
         ps = smem_p + (size_t)(grp * P.cslots + cslot) * P.p_slot_bytes;               \
     } while (0)
 #define WAIT_STORE_READS()                                                             \
     do {                                                                               \
-        if (P.cslots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); \
-        else               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
+        if (P.cslots == 2 && !P.cbatch) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); \
+        else                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
     } while (0)
         int par = 1;                                            // parity of this group's tile iteration
         uint64_t* cbar = &c_load_bar[grp];
+        // the bias slice of a CTA never changes when there is one problem, no per-image bias and one N tile per CTA:
+        // it is staged once instead of once per tile
+        const bool bias_static = P.nprob == 1 && P.prob[0].bias_img_stride == 0 && (P.prob[0].n_tiles == 1 || P.b_resident != 0);
+        if (bias_static) {
+            const IgemmProblem& q0 = P.prob[0];
+            const int n0 = (int)(blockIdx.x % q0.n_tiles) * P.n_out;
+            float* sb0 = s_bias + (grp * 2) * (512 / NG);
+            for (int i = etid; i < P.n_out; i += 128)
+                sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout : n0 + i));
+        }
+        const uint32_t smem_c_u32 = ptx::smem_u32(smem_c), smem_p_u32 = ptx::smem_u32(smem_p);
         // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
-#define EPI_BAR()                                                      \
-    do {                                                               \
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   \
-        else          asm volatile("bar.sync 2, 128;" ::: "memory");   \
+#define EPI_BAR()                                                           \
+    do {                                                                    \
+        if (grp == 0)      asm volatile("bar.sync 1, 128;" ::: "memory");   \
+        else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");   \
+        else if (grp == 2) asm volatile("bar.sync 3, 128;" ::: "memory");   \
+        else               asm volatile("bar.sync 4, 128;" ::: "memory");   \
     } while (0)
-        for (int t = blockIdx.x + grp * gridDim.x; t < P.total_tiles; t += 2 * gridDim.x) {
-            const TileCoord tc = decode_tile(P, t);
+        TileIter it;
+        for (it.init(P, blockIdx.x + grp * gridDim.x, NG * gridDim.x); it.valid(); it.next()) {
+            const TileCoord tc = it.coord(P);
             const IgemmProblem& q = P.prob[tc.pi];
             const int xoff = P.amode == AMODE_RS ? 1 : 0;           // RS: output column j sits at slab column j + 1
             const int y = tc.y0 + ty, x = tc.x0 + xoff + tx;
@@ -496,9 +590,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
             const bool valid = (y < q.H) && (x < q.W) && colok;
             const int srow = ty * P.VW + tx;                        // row inside the (CB, VW, TH) store box
             // bias of this tile, double-buffered by iteration parity (a slow thread may still read the previous one)
-            par ^= 1;
-            float* sb = s_bias[grp][par];
-            {
+            if (!bias_static) par ^= 1;
+            float* sb = s_bias + (grp * 2 + (bias_static ? 0 : par)) * (512 / NG);
+            if (!bias_static) {
                 const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
                 for (int i = etid; i < P.n_out; i += 128)
                     sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout : tc.n0 + i));
@@ -544,7 +638,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                                                            pack2(f[v * 8 + 4], f[v * 8 + 5], f16), pack2(f[v * 8 + 6], f[v * 8 + 7], f16));
                                 uint32_t off = (uint32_t)(srow * c_pitch + (c0 + v * 8) * 2);
                                 off ^= ((off >> 7) & swz_mask) << 4;
-                                *reinterpret_cast<uint4*>(cs + off) = o;
+                                sts128(ptx::smem_u32(cs) + off, o);
                             }
                         }
                     } else {
@@ -565,7 +659,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
                     if (P.pool) {
-                        pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                        pool_staged_tile(ptx::smem_u32(cs), ptx::smem_u32(ps), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                     }
@@ -582,39 +676,61 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                     q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 }
             } else if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+              // One staging tile per CB-channel chunk.  cbatch: the tile's chunks all have their own staging tile, so the
+              // whole accumulator is converted first and fence / barrier / TMA stores happen ONCE per tile; otherwise the
+              // chunks rotate through `cslots` tiles with a barrier pair per chunk.
+              const bool batch = P.cbatch != 0;
+              auto issue_store = [&](const uint8_t* c_tile, const uint8_t* p_tile, int mb, int c0) {
+                  const int n = tc.n0 + c0, yb = tc.y0 + mb * P.TH;
+                  const void* tm;
+                  int cch;
+                  if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
+                  else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
+                  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                               ::"l"((uint64_t)tm), "r"(ptx::smem_u32(c_tile)), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
+                  if (P.pool)
+                      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                   ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(p_tile)), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
+              };
               for (int mb = 0; mb < P.MT; ++mb) {                               // M-blocks of the tile (vertically stacked)
                 taddr = taddr0 + (uint32_t)(mb * P.BN);
-                const int yb = tc.y0 + mb * P.TH;
                 for (int c0 = 0; c0 < P.BN; c0 += P.CB) {
-                    if (c0 > 0 || mb > 0) {                                     // next staging tile: its store of two stores ago must be out
+                    if (!batch && (c0 > 0 || mb > 0)) {                         // next staging tile: the store that last used it must be out
                         if (etid == 0) WAIT_STORE_READS();
                         EPI_BAR();
                     }
-                    for (int cc = 0; cc < P.CB; cc += 32) {
-                        uint32_t r[32];
-                        const int ncol = min(32, P.CB - cc);
-                        if (ncol == 32) ptx::tmem_ld_32x32(taddr + c0 + cc, r);
-                        else            ptx::tmem_ld_32x16(taddr + c0 + cc, r);
-                        ptx::tmem_ld_wait();
+                    {
+                        // staged row of this thread: row_base + (column byte ^ xr); the TMA swizzle XORs address bits
+                        // 4..6 with bits 7..9, and a staged row never crosses a 128-byte line, so xr is per thread
+                        const uint32_t row_base = (uint32_t)(srow * c_pitch);
+                        const uint32_t xr = ((row_base >> 7) & swz_mask) << 4;
+                        const uint32_t cs_row = smem_c_u32 + (uint32_t)((grp * P.cslots + cslot) * P.c_slot_bytes) + row_base;
+                        const bool relu = q.relu != 0;
+                        auto convert8 = [&](const uint32_t* r8, int col) {           // 8 accumulator columns -> one 16-byte vector
+                            const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + col);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + col + 4);
+                            const float f0 = __uint_as_float(r8[0]) + b0.x, f1 = __uint_as_float(r8[1]) + b0.y;
+                            const float f2 = __uint_as_float(r8[2]) + b0.z, f3 = __uint_as_float(r8[3]) + b0.w;
+                            const float f4 = __uint_as_float(r8[4]) + b1.x, f5 = __uint_as_float(r8[5]) + b1.y;
+                            const float f6 = __uint_as_float(r8[6]) + b1.z, f7 = __uint_as_float(r8[7]) + b1.w;
+                            const uint4 o = relu ? make_uint4(pack2_relu<F16>(f0, f1), pack2_relu<F16>(f2, f3), pack2_relu<F16>(f4, f5), pack2_relu<F16>(f6, f7))
+                                                 : make_uint4(pack2(f0, f1, f16), pack2(f2, f3, f16), pack2(f4, f5, f16), pack2(f6, f7, f16));
+                            if (colok) sts128(cs_row + ((uint32_t)(col * 2) ^ xr), o);
+                        };
+                        if ((P.CB & 31) == 0) {
+                            for (int cc = 0; cc < P.CB; cc += 32) {
+                                uint32_t r[32];
+                                ptx::tmem_ld_32x32(taddr + c0 + cc, r);
+                                ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            if (v * 8 < ncol) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8);
-                                const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 8 + 4);
-                                float f[8];
-                                f[0] = __uint_as_float(r[v * 8 + 0]) + b0.x; f[1] = __uint_as_float(r[v * 8 + 1]) + b0.y;
-                                f[2] = __uint_as_float(r[v * 8 + 2]) + b0.z; f[3] = __uint_as_float(r[v * 8 + 3]) + b0.w;
-                                f[4] = __uint_as_float(r[v * 8 + 4]) + b1.x; f[5] = __uint_as_float(r[v * 8 + 5]) + b1.y;
-                                f[6] = __uint_as_float(r[v * 8 + 6]) + b1.z; f[7] = __uint_as_float(r[v * 8 + 7]) + b1.w;
-                                if (q.relu) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-                                }
-                                const uint4 o = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
-                                uint32_t off = (uint32_t)(srow * c_pitch + (cc + v * 8) * 2);
-                                off ^= ((off >> 7) & swz_mask) << 4;          // TMA swizzle pattern of the staging tile
-                                if (colok) *reinterpret_cast<uint4*>(cs + off) = o;
+                                for (int v = 0; v < 4; ++v) convert8(r + v * 8, cc + v * 8);
                             }
+                        } else {                                                     // CB == 16
+                            uint32_t r[32];
+                            ptx::tmem_ld_32x16(taddr + c0, r);
+                            ptx::tmem_ld_wait();
+                            convert8(r, 0);
+                            convert8(r + 8, 8);
                         }
                     }
                     if (c0 + P.CB >= P.BN && mb == P.MT - 1) {                // accumulator fully read: free the TMEM stage
@@ -622,28 +738,40 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_tc_kernel(const __grid
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    EPI_BAR();
-                    if (P.pool) {
-                        pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                    if (!batch) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
-                    }
-                    if (etid == 0) {
-                        const int n = tc.n0 + c0;
-                        const void* tm;
-                        int cch;
-                        if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
-                        else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
-                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"((uint64_t)tm), "r"(ptx::smem_u32(cs)), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
-                        if (P.pool)
-                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (P.pool) {
+                            pool_staged_tile(ptx::smem_u32(cs), ptx::smem_u32(ps), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            EPI_BAR();
+                        }
+                        if (etid == 0) {
+                            issue_store(cs, ps, mb, c0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                     }
                     NEXT_CSLOT();
                 }
+              }
+              if (batch) {                                                      // cslot is back at 0: chunk j sits in staging tile j
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                  EPI_BAR();
+                  uint8_t* c_base = smem_c + (size_t)(grp * P.cslots) * P.c_slot_bytes;
+                  uint8_t* p_base = smem_p + (size_t)(grp * P.cslots) * P.p_slot_bytes;
+                  if (P.pool) {
+                      for (int j = 0; j < P.cslots; ++j)
+                          pool_staged_tile(ptx::smem_u32(c_base) + (uint32_t)(j * P.c_slot_bytes), ptx::smem_u32(p_base) + (uint32_t)(j * P.p_slot_bytes), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                      EPI_BAR();
+                  }
+                  if (etid == 0) {
+                      int j = 0;
+                      for (int mb = 0; mb < P.MT; ++mb)
+                          for (int c0 = 0; c0 < P.BN; c0 += P.CB, ++j)
+                              issue_store(c_base + (size_t)j * P.c_slot_bytes, p_base + (size_t)j * P.p_slot_bytes, mb, c0);
+                      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  }
               }
             } else {
                 // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel

@@ -17,12 +17,12 @@ struct ProbeOut { long long issue, total; };
 // MODE 0: `if (threadIdx.x == 0)` single-thread role (divergent for the compiler: every UTCHMMA sits in a waterfall loop)
 // MODE 1: warp-uniform role (warp index broadcast with a shuffle), MMA / commit under elect.sync
 template <int MODE, int KC>
-__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int reps, ProbeOut* out) {
+__global__ void __launch_bounds__(128) mma_rate_kernel(int N, int reps, ProbeOut* out, int a_row_shift = 0, int swz = 128) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar, bar2[8];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < (20480 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
     if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) ptx::mbar_init(&bar2[i], 1); ptx::fence_mbar_init(); }
     if (threadIdx.x < 32) { ptx::tmem_alloc(&tmem_base_s, 256); ptx::tmem_relinquish(); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int N, int reps, ProbeOut
     if (MODE == 1 ? (warp_u == 0) : (threadIdx.x == 0)) {
         const uint32_t tm = tmem_base_s;
         const uint32_t idesc = ptx::make_idesc_f16(128, N, false);
-        const uint64_t da = ptx::make_kmajor_desc(ptx::smem_u32(smem), 128);
-        const uint64_t db = ptx::make_kmajor_desc(ptx::smem_u32(smem + 16384), 128);
+        const uint64_t da = ptx::make_kmajor_desc(ptx::smem_u32(smem) + (uint32_t)(a_row_shift * swz), swz);
+        const uint64_t db = ptx::make_kmajor_desc(ptx::smem_u32(smem + 20480), swz);
         int nc = 0;
         const long long t0 = clock64();
         for (int r = 0; r < reps; r += 4) {
@@ -151,7 +151,7 @@ int main() {
             for (int N : {16, 32, 64, 96, 128, 256}) {
                 ProbeOut h;
                 for (int it = 0; it < 2; ++it) {
-                    kern<<<148 * ctas, 128, 52 * 1024>>>(N, reps, d);
+                    kern<<<148 * ctas, 128, 60 * 1024>>>(N, reps, d, 0, 128);
                     CK(cudaDeviceSynchronize());
                 }
                 CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
@@ -162,6 +162,18 @@ int main() {
     run1(mma_rate_kernel<0, 1>, "if(thread==0), commit per 4    ");
     run1(mma_rate_kernel<1, 0>, "warp-uniform+elect, no commits ");
     run1(mma_rate_kernel<1, 1>, "warp-uniform+elect, commit per 4");
+    printf("# 1b. the same with the A descriptor starting `shift` pixel rows into the tile (row-shifted taps), 1 CTA/SM\n");
+    for (int swz : {128, 64})
+        for (int shift : {0, 1, 2, 8, 33})
+            for (int N : {32, 64, 96}) {
+                ProbeOut h;
+                for (int it = 0; it < 2; ++it) {
+                    mma_rate_kernel<1, 1><<<148, 128, 60 * 1024>>>(N, reps, d, shift, swz);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+                printf("swizzle %3d shift %2d N=%3d : total %.1f cycles per MMA\n", swz, shift, N, (double)h.total / reps);
+            }
     printf("# 2. row-shifted A descriptor (start row not a multiple of 8)\n");
     float* dout;
     CK(cudaMalloc(&dout, 128 * 64 * 4));
