@@ -47,6 +47,7 @@ SYMBOLS = [
     ("aau_frame_scores", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aau_best_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("aau_sigmoid", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("aau_device_fault", C.c_int, [C.c_void_p]),
     ("aau_num_launches", C.c_int, [C.c_void_p]),
     ("aau_op_profile", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_float),

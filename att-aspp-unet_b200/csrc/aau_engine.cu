@@ -1134,6 +1134,21 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
         if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
         cudaError_t r = op(a);
         if (r != cudaSuccess) return e.fail(AAU_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(r));
+#ifdef AAU_EPI_TIMING
+        if (prof) {                                                // tools only: per-launch role phase cycle counters
+            unsigned long long c[24];
+            cudaStreamSynchronize(a.stream);
+            cudaMemcpy(c, (char*)e.d_err + 64, sizeof(c), cudaMemcpyDeviceToHost);
+            cudaMemset((char*)e.d_err + 64, 0, sizeof(c));
+            fprintf(stderr, "[timing] %-70s mma:", plan->info[n].name.c_str());
+            for (int i = 0; i < 4; ++i) fprintf(stderr, " %llu", c[i]);
+            fprintf(stderr, " | epi g0:");
+            for (int i = 8; i < 16; ++i) fprintf(stderr, " %llu", c[i]);
+            fprintf(stderr, " | epi g1:");
+            for (int i = 16; i < 24; ++i) fprintf(stderr, " %llu", c[i]);
+            fprintf(stderr, "\n");
+        }
+#endif
         ++n;
     }
     if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
@@ -1165,6 +1180,17 @@ int aau_frame_scores(aau_handle* h, const void* logits, int input_kind, int N, i
         area_argmax_kernel<<<1, 1024, 0, s>>>(areas, N, best);
         AAU_CUDA(cudaGetLastError());
     }
+    return AAU_OK;
+}
+
+int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!logits || !prob || n < 1) return e.fail(AAU_ERR_INVALID, "bad sigmoid arguments");
+    cudaSetDevice(e.device);
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)e.num_sms * 8);
+    sigmoid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, (long long)n, prob);
+    AAU_CUDA(cudaGetLastError());
     return AAU_OK;
 }
 

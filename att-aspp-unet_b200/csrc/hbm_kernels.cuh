@@ -317,6 +317,12 @@ __global__ void __launch_bounds__(256) frame_area_kernel(const float* __restrict
     }
 }
 
+// prob = sigmoid(logits), fp32 -> fp32 (model_attention_aspp.py:54 `torch.sigmoid(self.net(...))`), same expression as `above()`
+__global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = 1.f / (1.f + expf(-__ldg(x + i)));
+}
+
 // `mask_3d.sum((1,2))` on a uint8 volume (model_attention_aspp.py:94): per-frame sum of byte VALUES (equal to the
 // area for {0,1} masks); optional binarised copy `(v > 0)` (model_attention_aspp.py:97).
 __global__ void __launch_bounds__(256) frame_sum_u8_kernel(const uint8_t* __restrict__ vol, int HW, int* __restrict__ sums,

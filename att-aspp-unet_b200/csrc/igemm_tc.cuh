@@ -57,6 +57,18 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+// Optional phase timing (build with -DAAU_EPI_TIMING; tools only): cycle counters per role phase, accumulated
+// into the 24 uint64 slots behind the error flag and dumped per launch by the engine in profile mode.
+#ifdef AAU_EPI_TIMING
+#define TM_DECL() long long tm_mark_ = clock64(); unsigned long long tm_acc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TM_MARK(i) do { const long long n_ = clock64(); tm_acc_[i] += (unsigned long long)(n_ - tm_mark_); tm_mark_ = n_; } while (0)
+#define TM_FLUSH(base, cond) do { if (cond) { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(reinterpret_cast<unsigned long long*>(P.err + 16) + (base) + i_, tm_acc_[i_]); } } while (0)
+#else
+#define TM_DECL() do {} while (0)
+#define TM_MARK(i) do {} while (0)
+#define TM_FLUSH(base, cond) do {} while (0)
+#endif
+
 namespace aau {
 
 enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
@@ -310,11 +322,14 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     const bool res = P.b_resident != 0;
     if (res) ptx::mbar_wait(b_res_bar, 0, P.err, ERR_MMA_WAIT_FULL);
     TileIter it;
+    TM_DECL();
     for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
         const TileCoord tc = it.coord(P);
         const IgemmProblem& q = P.prob[tc.pi];
+        TM_MARK(2);
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
         ptx::tc_fence_after();
+        TM_MARK(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN * P.MT);
         uint32_t accumulate = 0;
         if (P.amode == AMODE_TAP) {
@@ -337,8 +352,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         } else if (P.amode == AMODE_RS) {
             const uint32_t row16 = (uint32_t)swz >> 4;                        // one pixel row of the slab, in 16-byte units
             for (int ch = 0; ch < q.nchunk; ++ch) {
+                TM_MARK(2);
                 ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
+                TM_MARK(1);
                 if (ptx::elect_one()) {
                     const uint32_t a_lo = a_base + ia * a_slot16;
 #pragma unroll
@@ -349,6 +366,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                     ptx::umma_commit(&empty_a[ia]);
                 }
                 __syncwarp();
+                TM_MARK(3);
                 accumulate = 1;
                 if (++ia == P.nA) { ia = 0; pa ^= 1; }
             }
@@ -383,6 +401,8 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         __syncwarp();
         if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    TM_MARK(2);
+    TM_FLUSH(0, (threadIdx.x & 31) == 0);
 }
 
 // NG = epilogue groups = TMEM accumulator stages (2, or 4 for single-CTA-per-SM layers whose 4 accumulators fit in
@@ -581,6 +601,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         else               asm volatile("bar.sync 4, 128;" ::: "memory");   \
     } while (0)
         TileIter it;
+        TM_DECL();
         for (it.init(P, blockIdx.x + grp * gridDim.x, NG * gridDim.x); it.valid(); it.next()) {
             const TileCoord tc = it.coord(P);
             const IgemmProblem& q = P.prob[tc.pi];
@@ -597,11 +618,15 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 for (int i = etid; i < P.n_out; i += 128)
                     sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout : tc.n0 + i));
             }
+            TM_MARK(0);                                         // 0: tile bookkeeping
             if (etid == 0) WAIT_STORE_READS();                  // the store that last used the next staging tile has left smem
+            TM_MARK(1);                                         // 1: wait for the previous TMA store to have read its tile
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
             acc_phase ^= 1;
             ptx::tc_fence_after();
+            TM_MARK(2);                                         // 2: wait for the accumulator
             EPI_BAR();                                          // bias visible, staging tiles free
+            TM_MARK(3);                                         // 3: group barrier at the top
             const uint32_t taddr0 = tmem_base + (uint32_t)(acc * P.BN * P.MT) + ((uint32_t)(quarter * 32) << 16);
             uint32_t taddr = taddr0;
 
@@ -738,18 +763,22 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                     }
+                    TM_MARK(4);                                                 // 4: TMEM -> registers -> staged tile
                     if (!batch) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
+                        TM_MARK(5);                                             // 5: proxy fence + barrier
                         if (P.pool) {
                             pool_staged_tile(ptx::smem_u32(cs), ptx::smem_u32(ps), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             EPI_BAR();
+                            TM_MARK(6);                                         // 6: pooling + fence + barrier
                         }
                         if (etid == 0) {
                             issue_store(cs, ps, mb, c0);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
+                        TM_MARK(7);                                             // 7: TMA store issue
                     }
                     NEXT_CSLOT();
                 }
@@ -832,6 +861,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
             }
         }
+        TM_FLUSH(8 + 8 * (grp & 1), lane == 0 && quarter == 0);
 #undef EPI_BAR
 #undef NEXT_CSLOT
 #undef WAIT_STORE_READS

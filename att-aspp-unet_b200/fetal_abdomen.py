@@ -31,7 +31,53 @@ except ImportError:                                     # package-style import
     from . import _capi                                 # type: ignore
     from .attention_aspp_unet import AttentionASPPUNet  # type: ignore
 
-__all__ = ["FetalAbdomenSegmentation", "select_fetal_abdomen_mask_and_frame", "merge_shard_scores", "largest_component"]
+__all__ = ["FetalAbdomenSegmentation", "select_fetal_abdomen_mask_and_frame", "merge_shard_scores", "largest_component",
+           "preprocess_sweep", "load_image_file_as_array", "crop_roi_224"]
+
+ROI = 224                                               # model_attention_aspp.py:20-30
+N_SAMPLED_FRAMES = 128                                  # model_attention_aspp.py:45
+
+
+def preprocess_sweep(frames: np.ndarray) -> np.ndarray:
+    """Per-frame min-max stretch to uint8, CLAHE (clip 1.0, 8x8 tiles), 3x3 median, ``/255`` -- the reference's
+    input conditioning (model_attention_aspp.py:11-17, inference.py:147-190).  Host OpenCV calls, the same ones
+    the reference makes (SURVEY.md section 8 f3 lists a GPU version as a later row).  Returns float32 [N,H,W]."""
+    import cv2
+    clahe = cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8, 8))
+    out = np.empty(frames.shape, np.float32)
+    for i, sl in enumerate(frames):
+        u8 = cv2.normalize(sl, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+        out[i] = cv2.medianBlur(clahe.apply(u8), 3)
+    out /= 255.0
+    return out
+
+
+def load_image_file_as_array(*, location) -> np.ndarray:
+    """``[1, N, H, W]`` float32 in [0,1] from a .mha sweep (model_attention_aspp.py:11-17)."""
+    try:
+        from metaimage import read_mha
+    except ImportError:
+        from .metaimage import read_mha                 # type: ignore
+    arr, _ = read_mha(location)
+    if arr.ndim != 3:
+        raise ValueError(f"Expected 3-D image (frames, H, W), got {arr.shape}")
+    return preprocess_sweep(arr)[None]
+
+
+def crop_roi_224(img: np.ndarray):
+    """224x224 patch centred on the centroid of the pixels brighter than 1.2x the frame mean, clamped to the
+    frame, zero-padded when the frame is smaller (model_attention_aspp.py:20-30).  Returns ``(patch, (x0, y0))``."""
+    h, w = img.shape
+    ys, xs = np.where(img > img.mean() * 1.2)
+    cx, cy = (w // 2, h // 2) if len(xs) == 0 else (int(xs.mean()), int(ys.mean()))
+    x0, y0 = max(0, cx - ROI // 2), max(0, cy - ROI // 2)
+    x0, y0 = min(x0, w - ROI), min(y0, h - ROI)
+    patch = img[y0:y0 + ROI, x0:x0 + ROI]
+    if patch.shape != (ROI, ROI):
+        full = np.zeros((ROI, ROI), img.dtype)
+        full[:patch.shape[0], :patch.shape[1]] = patch
+        patch = full
+    return patch, (x0, y0)
 
 
 def largest_component(frame: np.ndarray) -> np.ndarray:
@@ -195,6 +241,50 @@ class FetalAbdomenSegmentation:
         out["best_idx"] = lo + bi
         self.last = out
         return out
+
+    @torch.no_grad()
+    def predict(self, input_img_path, save_probabilities: bool = False) -> np.ndarray:
+        """The reference wrapper's ``predict`` (model_attention_aspp.py:41-65): read the sweep, condition every frame,
+        sample 128 frames (``linspace``), crop a 224x224 ROI per frame, run the network + sigmoid, paste the ROI
+        probabilities back (``cv2.resize`` to the ROI extent) into a zero ``[128, H, W]`` float32 volume.
+        ``input_img_path`` is the list ``inference.py`` passes (first entry is used)."""
+        import cv2
+        from pathlib import Path
+        path = Path(input_img_path[0] if isinstance(input_img_path, (list, tuple)) else input_img_path)
+        self.case_id = path.stem
+        vol = load_image_file_as_array(location=path)
+        return self.predict_array(vol[0], save_probabilities=save_probabilities)
+
+    @torch.no_grad()
+    def predict_array(self, frames01: np.ndarray, save_probabilities: bool = False) -> np.ndarray:
+        """``predict`` from an already conditioned float32 ``[N, H, W]`` volume in [0,1]."""
+        import cv2
+        from pathlib import Path
+        idxs = np.linspace(0, frames01.shape[0] - 1, N_SAMPLED_FRAMES).astype(int)
+        vol = frames01[idxs]
+        N, H, W = vol.shape
+        patches, coords = [], []
+        for sl in vol:
+            p, xy = crop_roi_224(sl)
+            patches.append(p)
+            coords.append(xy)
+        x = torch.from_numpy(np.stack(patches)).unsqueeze(1).to(self.device)      # [128,1,224,224] float32
+        prob = torch.empty((N, ROI, ROI), dtype=torch.float32, device=self.device)
+        B = max(1, self.batch)
+        for i in range(0, N, B):
+            logits = self._net_logits(x[i:i + B])
+            st = _capi.lib().aau_sigmoid(self.net.engine_handle(), logits.data_ptr(), logits.numel(), prob[i:i + B].data_ptr(),
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+            _capi.check(self.net.engine_handle(), st, "aau_sigmoid")
+        prob_roi = prob.cpu().numpy()
+        prob_full = np.zeros((N, H, W), np.float32)
+        for i, (x0, y0) in enumerate(coords):
+            h_roi, w_roi = min(ROI, H - y0), min(ROI, W - x0)
+            prob_full[i, y0:y0 + h_roi, x0:x0 + w_roi] = cv2.resize(prob_roi[i], (w_roi, h_roi))
+        if save_probabilities:
+            Path("output/probabilities").mkdir(parents=True, exist_ok=True)
+            np.save(f"output/probabilities/{getattr(self, 'case_id', 'case')}_prob.npy", prob_full)
+        return prob_full
 
     def _mask_from_logits(self, logits_1hw: torch.Tensor, thr: float) -> np.ndarray:
         _, H, W = logits_1hw.shape

@@ -110,6 +110,10 @@ int aau_frame_scores(aau_handle* h, const void* values, int input_kind, int N, i
  * aau_frame_scores calls of a sweep, and on the host-gathered scores of a multi-GPU run.  Asynchronous. */
 int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream);
 
+/* prob[i] = 1 / (1 + exp(-logits[i])), device fp32 -> device fp32, n elements: the `torch.sigmoid(self.net(x))` of
+ * model_attention_aspp.py:54 for callers that want the probability volume itself (`predict`).  Asynchronous. */
+int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void* stream);
+
 /* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
  * the device. */
 int aau_device_fault(aau_handle* h);

@@ -27,6 +27,10 @@ Reference lines restated (all paths relative to /root/reference):
   select_fetal_abdomen_mask_and_frame   model_attention_aspp.py:91-97
   predict_prob_tta     attention_aspp_unet_pipeline_stage.py:336-338
   convert_2d_mask_to_3d inference.py:257-273
+  load_image_file_as_array (frame conditioning)   model_attention_aspp.py:11-17
+  crop_roi_224         model_attention_aspp.py:20-30
+  FetalAbdomenSegmentation.predict (sample 128, ROI, batch 8, paste back)   model_attention_aspp.py:41-65
+  write_array_as_image_file (volume semantics)    inference.py:208-254
 """
 from __future__ import annotations
 
@@ -352,8 +356,7 @@ def select_fetal_abdomen_mask_and_frame(mask_3d: np.ndarray):
 
 def convert_2d_mask_to_3d(mask_2d: np.ndarray, frame_number: int, number_of_frames: int) -> np.ndarray:
     """inference.py:257-273: 1->2 relabel, all-zero volume when frame_number == -1, ValueError out of range."""
-    mask_2d = mask_2d.copy()
-    mask_2d[mask_2d == 1] = 2
+    mask_2d = np.where(mask_2d == 1, 2, 0).astype(np.uint8)
     vol = np.zeros((number_of_frames, mask_2d.shape[0], mask_2d.shape[1]), dtype=np.uint8)
     if frame_number == -1:
         return vol
@@ -361,6 +364,62 @@ def convert_2d_mask_to_3d(mask_2d: np.ndarray, frame_number: int, number_of_fram
         vol[frame_number] = mask_2d
         return vol
     raise ValueError("frame_number out of range")
+
+
+# --------------------------------------------------------------------------------------------
+# wrapper path around the network: conditioning, ROI-224 predict, output volume
+# --------------------------------------------------------------------------------------------
+def condition_frames(frames: np.ndarray) -> np.ndarray:
+    """model_attention_aspp.py:11-17: min-max -> uint8, CLAHE(1.0, 8x8), median 3, /255 (float32 [N,H,W])."""
+    import cv2
+    clahe = cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8, 8))
+    stack = [cv2.medianBlur(clahe.apply(cv2.normalize(sl, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)), 3) for sl in frames]
+    return np.stack(stack).astype(np.float32) / 255.0
+
+
+def crop_roi_224(img: np.ndarray):
+    """model_attention_aspp.py:20-30."""
+    import cv2
+    h, w = img.shape
+    thr = img.mean() * 1.2
+    ys, xs = np.where(img > thr)
+    cx, cy = (w // 2, h // 2) if len(xs) == 0 else (int(xs.mean()), int(ys.mean()))
+    x0, y0 = max(0, cx - 112), max(0, cy - 112)
+    x0, y0 = min(x0, w - 224), min(y0, h - 224)
+    patch = img[y0:y0 + 224, x0:x0 + 224]
+    if patch.shape != (224, 224):
+        patch = cv2.copyMakeBorder(patch, 0, 224 - patch.shape[0], 0, 224 - patch.shape[1], cv2.BORDER_CONSTANT, value=0)
+    return patch, (x0, y0)
+
+
+def predict_roi224(sd, frames01: np.ndarray, cfg: NetCfg = NetCfg(base_c=16)) -> np.ndarray:
+    """FetalAbdomenSegmentation.predict after the file read (model_attention_aspp.py:44-60): float32 [128,H,W]."""
+    import cv2
+    vol = frames01[None]
+    idxs = np.linspace(0, vol.shape[1] - 1, 128).astype(int)
+    vol = vol[:, idxs]
+    N, H, W = vol.shape[1:]
+    patches, coords = [], []
+    for sl in vol[0]:
+        p, xy = crop_roi_224(sl)
+        patches.append(p)
+        coords.append(xy)
+    tensor = torch.from_numpy(np.stack(patches)).unsqueeze(1)
+    with torch.no_grad():
+        outs = [torch.sigmoid(forward(sd, tensor[i:i + 8], cfg)).squeeze(1) for i in range(0, N, 8)]
+    prob_roi = torch.cat(outs).numpy()
+    prob_full = np.zeros((N, H, W), np.float32)
+    for i, (x0, y0) in enumerate(coords):
+        h_roi, w_roi = min(224, H - y0), min(224, W - x0)
+        prob_full[i, y0:y0 + h_roi, x0:x0 + w_roi] = cv2.resize(prob_roi[i], (w_roi, h_roi))
+    return prob_full
+
+
+def output_volume(mask_2d: np.ndarray, frame_number: int, number_of_frames: int) -> np.ndarray:
+    """The uint8 volume write_array_as_image_file hands to SimpleITK (inference.py:221-230): relabel 1->2, place
+    the frame, then `> 0.5 -> 1`."""
+    vol = convert_2d_mask_to_3d(np.squeeze(mask_2d).astype(np.float32), frame_number, number_of_frames)
+    return np.where(vol > 0.5, 1, 0).astype(np.uint8)
 
 
 # --------------------------------------------------------------------------------------------
