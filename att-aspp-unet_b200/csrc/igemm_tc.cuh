@@ -361,7 +361,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {                       // B resident, TAP order: slot tap*nchunk + ch
                         const uint32_t shift = (uint32_t)((tap / 3) * P.TW + (tap % 3)) * row16;
-                        mma_subblock<KK>(d_tmem, a_lo + shift, b_base + (uint32_t)(tap * q.nchunk + ch) * b_slot16, desc_hi, idesc, tap == 0 ? accumulate : 1u);
+                        const uint32_t b_lo = b_base + (uint32_t)(tap * q.nchunk + ch) * b_slot16;
+                        if (P.MT == 2)                                        // second M-block: TH rows further down the slab
+                            mma_subblock<KK>(d_tmem + P.BN, a_lo + shift + a_mb16, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
+                        mma_subblock<KK>(d_tmem, a_lo + shift, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
                     }
                     ptx::umma_commit(&empty_a[ia]);
                 }
@@ -453,6 +456,10 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // Programmatic dependent launch: let the next kernel of the stream be scheduled onto SMs as our CTAs retire (its
+    // barrier / TMEM set-up and resident-weight load then overlap our tail); every role that touches activations
+    // first executes griddepcontrol.wait, which returns once the PREVIOUS kernel has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -482,6 +489,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 __syncwarp();
             }
+            asm volatile("griddepcontrol.wait;" ::: "memory");                // weights are constants; activations are not
             TileIter it;
             for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
                 const TileCoord tc = it.coord(P);
@@ -592,6 +600,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout : n0 + i));
         }
         const uint32_t smem_c_u32 = ptx::smem_u32(smem_c), smem_p_u32 = ptx::smem_u32(smem_p);
+        asm volatile("griddepcontrol.wait;" ::: "memory");          // before the first store / activation read of this role
         // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
 #define EPI_BAR()                                                           \
     do {                                                                    \

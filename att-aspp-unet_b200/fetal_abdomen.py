@@ -135,7 +135,7 @@ class FetalAbdomenSegmentation:
     PROB_THRESHOLD = 0.05                                  # model_attention_aspp.py:71
 
     def __init__(self, checkpoint_path: Optional[str] = None, *, net: Optional[AttentionASPPUNet] = None, base: int = 16,
-                 device: str | torch.device = "cuda", batch: int = 28, act_dtype: str = "bf16"):
+                 device: str | torch.device = "cuda", batch: int = 56, act_dtype: str = "bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("FetalAbdomenSegmentation (B200 engine) needs a CUDA device; there is no CPU fallback")
         self.device = torch.device(device)

@@ -266,8 +266,17 @@ def run_engine(args):
     fps_e2e = frames_total / (ms_e2e / 1e3)
     tc_tflops = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     fwd_ms = sum(v["ms"] for v in layer_rows.values()) / max(nb, 1)
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "r01_igemm_dram_traffic.json"          # ncu --set full capture of the igemm launches of one forward
+    if tp.exists():
+        try:
+            tj = json.loads(tp.read_text())
+            traffic = tj["dram_bytes_per_frame"] * B                 # per forward of this bench's batch, like `achieved`
+            traffic_src = f"ncu dram__bytes_read+write summed over the {tj['launches']} igemm launches of one forward: {tj['dram_bytes_per_frame'] / 1e6:.0f} MB per frame (profiles/r01_igemm_dram_traffic.json) x batch"
+        except Exception:
+            pass
     roof = {"bound": "tensor", "achieved": tc_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tc_tflops / pk["tc_sustained"],
-            "traffic": None, "kernel": "igemm_tc_kernel", "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
+            "traffic": traffic, "traffic_note": traffic_src, "kernel": "igemm_tc_kernel", "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
             "note": f"algorithmic FLOPs of the {n_tc} igemm_tc_kernel launches of one forward / their summed CUDA-event time; "
                     f"they are {tc_ms / max(sum(v['ms'] for v in layer_rows.values()), 1e-9):.0%} of the forward",
             "whole_forward_tflops": fps / world * GFLOP_PER_FRAME / 1e3, "whole_forward_frac": fps / world * GFLOP_PER_FRAME / 1e3 / pk["tc_sustained"]}
@@ -303,7 +312,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=28)
+    ap.add_argument("--batch", type=int, default=56, help="frames per forward (a divisor of 840)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (amode, resident, ctas)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
