@@ -191,7 +191,10 @@ class AttentionASPPUNet(nn.Module):
             self._weights_version = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:                                # interpreter shutdown: torch's module machinery may already be gone
+            pass
 
     def _float_entries(self):
         for key, tensor in self.state_dict(keep_vars=True).items():
@@ -312,7 +315,7 @@ class AttentionASPPUNet(nn.Module):
         ``set_option("profile", 1)`` was active).  Synchronises."""
         L = _capi.lib()
         rows = []
-        for i in range(self.num_launches()):
+        for i in range(L.aau_num_ops(self._handle)):
             layer, kern = C.c_char_p(), C.c_char_p()
             ms, fl, by = C.c_float(), C.c_double(), C.c_double()
             _capi.check(self._handle, L.aau_op_profile(self._handle, i, C.byref(layer), C.byref(kern), C.byref(ms), C.byref(fl), C.byref(by)),

@@ -1268,6 +1268,7 @@ int aau_device_fault(aau_handle* h) {
 }
 
 int aau_num_launches(const aau_handle* h) { return h ? h->e.last_launches : 0; }
+int aau_num_ops(const aau_handle* h) { return (h && h->e.last_plan) ? (int)h->e.last_plan->ops.size() : 0; }
 
 int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel, float* ms, double* flops, double* bytes) {
     if (!h) return AAU_ERR_INVALID;

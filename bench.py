@@ -32,6 +32,25 @@ GFLOP_PER_FRAME = 160.319          # SURVEY.md section 8d / BASELINE.md section 
 METRIC = "frames/sec Att-ASPP-UNet fwd (744x562 US)"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL and friends print banners there) and keep the real stdout for the
+    ONE JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -137,7 +156,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count(), "torch": torch.__version__},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -301,7 +320,7 @@ def run_engine(args):
             "selected_frame": {"device_arm": best_dev[0], "e2e_arm": res["best_idx"], "area": res["best_area"]}}
     if world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, frames=args.cpu_frames)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -318,11 +337,12 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample of the engine arm")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the engine has no CPU fallback"}))
+        emit({"error": "no CUDA device: the engine has no CPU fallback"})
         sys.exit(2)
     run_engine(args)
 

@@ -120,7 +120,9 @@ int aau_device_fault(aau_handle* h);
 
 /* Debug / measurement aids. */
 int aau_num_launches(const aau_handle* h);          /* kernels launched by the last aau_forward */
-/* Per-launch record of the LAST aau_forward: i in [0, aau_num_launches).  `layer` = the reference layer the
+int aau_num_ops(const aau_handle* h);               /* stream operations of the last aau_forward: its kernels plus stream-ordering
+                                                        steps (the side-stream join of the ASPP image-pooling branch) */
+/* Per-operation record of the LAST aau_forward: i in [0, aau_num_ops).  `layer` = the reference layer the
  * launch implements, `kernel` = kernel symbol, `flops` / `bytes` = its algorithmic work (2*MAC with dense tap
  * count; activations in + out + weights once).  `ms` is the CUDA-event time between this launch and the next on
  * the caller's stream when aau_set_option("profile", 1) was on during that forward, else -1 (synchronises). */

@@ -228,3 +228,35 @@ def test_sweep_engine_matches_oracle_selection():
     assert np.array_equal(seg.frame_mask(vol, gidx, 0.5), m2)
     empty = seg.segment_sweep(np.zeros((3, 96, 128), np.uint8), prob_thr=0.999999)
     assert empty["best_idx"] == -1 and empty["mask"].sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ planner options
+# Every staging / pipelining variant of the implicit-GEMM kernel must give the same network: the planner picks among
+# them per layer by shape, so each is forced here on shapes small enough for the oracle (fp16 storage: tight bound).
+OPTION_SETS = [
+    {"rs": 0},                      # dx-stacked (AMODE_DXN) instead of row-shifted taps
+    {"rs": 0, "amode": 1},          # column-shifted slabs for every 3x3 layer
+    {"amode": 0},                   # one TMA box per tap
+    {"rs_mt": 2},                   # 256-pixel row-shifted tiles everywhere
+    {"ng": 4, "ctas": 1},           # four accumulator stages / epilogue groups, one CTA per SM
+    {"ng": 2, "ctas": 1, "cslots": 1},
+    {"resident": 0},                # weights streamed through the B ring
+    {"titer": 0, "pdl": 0, "side": 0, "fusepool": 0},
+]
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_planner_variants_agree(opts):
+    cfg = O.NetCfg(base_c=32)
+    sd, x = r1_case(cfg, (3, 141, 186), seed=5)
+    ref = O.forward(sd, x, cfg)
+    net = make_net(cfg, sd, "fp16")
+    base = net(x.cuda()).cpu()
+    for k, v in opts.items():
+        net.set_option(k, v)
+    out = net(x.cuda()).cpu()
+    net.check_device()
+    spread = ref.std().item()
+    assert (out - ref).abs().max().item() <= 0.03 * spread + 2e-2, f"{opts}: differs from the oracle"
+    assert (out - base).abs().max().item() <= 0.03 * spread + 2e-2, f"{opts}: differs from the default plan"
+    assert agreement(out, ref, 0.5) >= 0.995
