@@ -68,6 +68,9 @@ struct ConvDesc {             // one GEMM problem
     int convt_cout = 0;
     float* aux = nullptr;
     int gate_plus_x = 0;
+    int fix_axis = -1;        // CONVTFIX: 0 = H, 1 = W
+    const float* fix_coef = nullptr;
+    int fix_cc = 0;           // CONVTFIX: channels per column block (a multiple of 16 that divides Cout, <= 64)
 };
 
 struct FwdArgs {
@@ -117,6 +120,8 @@ struct Engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_side = 1;
     int opt_pdl = 1;
+    int opt_fusefix = 1;
+    int opt_fixcc = 0;
     int last_launches = 0;
     int opt_amode = -1;
     int opt_resident = 1;
@@ -468,6 +473,58 @@ static int commit_weights(Engine& e) {
     return AAU_OK;
 }
 
+// ConvTranspose2d(2,2) fused with the one-axis bilinear fix-up (igemm_tc.cuh, EPI_CONVTFIX).  Rows of B, per n tile
+// (phase t along the free axis, channel block cb of CC channels): [up | mid0 | mid1], K = (tap -1, tap 0) x Cin with
+//   up  [c][      i] = W[i][cb*CC+c][fixed phase 1][t]   (tap -1)
+//   mid0[c][Cin + i] = W[i][cb*CC+c][fixed phase 0][t]   (tap  0)
+//   mid1[c][Cin + i] = W[i][cb*CC+c][fixed phase 1][t]   (tap  0)
+// and zeros elsewhere.  Built on first use of a shape that needs it (the odd-size axis is only known then).
+static const GemmW* prep_upfix(Engine& e, int lvl, int axis, int cc) {
+    const std::string p = "u" + std::to_string(lvl);
+    const std::string name = p + ".upfix" + (axis == 0 ? "H" : "W");
+    auto it = e.gw.find(name);
+    if (it != e.gw.end()) return &it->second;
+    auto w = e.host.find(p + ".up.weight"), b = e.host.find(p + ".up.bias");
+    if (w == e.host.end() || b == e.host.end()) return nullptr;
+    const int c = e.cfg.base_c, out_c = c << (lvl - 1), in_c = 2 * out_c;
+    GemmW g;
+    g.N = 6 * out_c; g.Cin = in_c; g.taps = 2; g.K = 2 * in_c;
+    std::vector<float> Bm((size_t)g.N * g.K, 0.f);
+    const int nsub = out_c / cc;
+    auto W = [&](int i, int co, int a, int bb) { return w->second[((size_t)i * out_c + co) * 4 + a * 2 + bb]; };
+    for (int t = 0; t < 2; ++t)
+        for (int cb = 0; cb < nsub; ++cb)
+            for (int blk = 0; blk < 3; ++blk)
+                for (int cch = 0; cch < cc; ++cch) {
+                    const size_t row = (((size_t)(t * nsub + cb) * 3 + blk) * cc + cch) * g.K;
+                    const int co = cb * cc + cch, fixed_phase = blk == 1 ? 0 : 1, tap = blk == 0 ? 0 : 1;
+                    for (int i = 0; i < in_c; ++i)
+                        Bm[row + (size_t)tap * in_c + i] = axis == 0 ? W(i, co, fixed_phase, t) : W(i, co, t, fixed_phase);
+                }
+    if (finish_gemm(e, g, Bm, b->second) != AAU_OK) return nullptr;
+    e.gw[name] = g;
+    return &e.gw[name];
+}
+
+// ATen's upsample_bilinear2d source indices / weights (align_corners = false) for `out` positions over `in` samples,
+// re-expressed on the three transposed-conv rows a GEMM row j holds (2j-1, 2j, 2j+1): coef[o][k], o = 2j + p.
+static bool fix_coefficients(int in, int out, std::vector<float>& coef) {
+    coef.assign((size_t)out * 3, 0.f);
+    const float scale = (float)in / (float)out;
+    for (int o = 0; o < out; ++o) {
+        float src = scale * ((float)o + 0.5f) - 0.5f;
+        if (src < 0.f) src = 0.f;
+        const int i0 = (int)src, i1 = std::min(i0 + 1, in - 1);
+        const float w1 = src - (float)i0, w0 = 1.f - w1;
+        const int base = 2 * (o >> 1) - 1;                          // transposed-conv row held in block `up`
+        const int k0 = i0 - base, k1 = i1 - base;
+        if (k0 < 0 || k0 > 2 || k1 < 0 || k1 > 2) return false;   // not a one-sample fix-up
+        coef[(size_t)o * 3 + k0] += w0;
+        coef[(size_t)o * 3 + k1] += w1;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // plan building
 // ------------------------------------------------------------------------------------------------------------
@@ -530,6 +587,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     if (!BN) return e.fail(AAU_ERR_INVALID, "output channels must be a multiple of 16");
     if (d0.epi == EPI_GATE || d0.epi == EPI_OUTCONV)
         if (BN != Ntot) return e.fail(AAU_ERR_INVALID, "gate / out_conv epilogues need all channels in one tile");
+    const bool cfix = d0.epi == EPI_CONVTFIX;
+    if (cfix) BN = 3 * d0.fix_cc;                                  // [up | mid0 | mid1] of one channel block
     const bool want_pool = d0.pool_out.p != nullptr && d0.epi == EPI_STORE && descs.size() == 1;
     const bool conv3 = d0.w->taps == 9;
     bool slab = conv3 && d0.dil == 1 && BN <= e.opt_slab_max_bn;
@@ -558,7 +617,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.BN = BN;
     P.n_out = n_out;
     // tile shape: minimise padded pixels (and, for slabs, halo overhead)
-    const int H = d0.in.H, W = d0.in.W;
+    // (the fused transposed-conv + fix-up GEMM has one extra row / column: output 2n holds transposed-conv row 2n-1)
+    const int H = d0.in.H + (cfix && d0.fix_axis == 0 ? 1 : 0), W = d0.in.W + (cfix && d0.fix_axis == 1 ? 1 : 0);
     double best = 1e30;
     for (int tw = 8; tw <= 128; tw <<= 1) {
         const int th = 128 / tw;
@@ -585,10 +645,10 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.b_slot_bytes = BN * swz;
     P.a_slot_bytes = slab ? (((P.TH * P.MT + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
     // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
-    const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE;
-    const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : n_out);
+    const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE || cfix;
+    const int cdiv = d0.epi == EPI_CONVT ? d0.convt_cout : (d0.epi == EPI_GATE ? d0.out.C : (cfix ? BN / 3 : n_out));
     P.CB = cdiv % 64 == 0 ? 64 : (cdiv % 32 == 0 ? 32 : 16);
-    if (d0.epi != EPI_GATE && n_out % P.CB) P.CB = 16;
+    if (d0.epi != EPI_GATE && !cfix && n_out % P.CB) P.CB = 16;
     P.c_slot_bytes = 128 * P.CB * 2;
     P.pool = want_pool ? 1 : 0;
     P.p_slot_bytes = want_pool ? ((((P.TH / 2) * (P.VW / 2) * P.CB * 2) + 1023) & ~1023) : 0;
@@ -598,7 +658,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // CTA fits and four accumulators fit in the 512 TMEM columns, that CTA runs 4 stages / groups instead.
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
     // n_tiles so that the static striding keeps every CTA on the same N tile
-    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn) && e.opt_resident != 0;
+    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0;
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
     auto cols_for = [&](int stages) { int c = 32; while (c < stages * BN * P.MT) c <<= 1; return c; };
     int ctas = (BN <= 128) ? 2 : 1;                               // measured: 2 CTAs co-reside, a third only queues
@@ -622,8 +682,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
                 if (rs && !res) continue;                          // row-shifted taps index the resident weight matrix
                 const int sel = pass % 3;
                 const bool cbatch = sel == 0;
-                if (cbatch && !((d0.epi == EPI_STORE || d0.epi == EPI_CONVT) && nchunks >= 2 && nchunks <= 4 && e.opt_cslots == 0)) continue;
-                const int cslots = cbatch ? nchunks : (sel == 1 ? 2 : 1);
+                if (cfix && (!cbatch || !res)) continue;           // both phases of a chunk are staged side by side; weights resident
+                if (cbatch && !cfix && !((d0.epi == EPI_STORE || d0.epi == EPI_CONVT) && nchunks >= 2 && nchunks <= 4 && e.opt_cslots == 0)) continue;
+                const int cslots = cfix ? 2 : (cbatch ? nchunks : (sel == 1 ? 2 : 1));
                 if (sel == 1 && (!tma_out || e.opt_cslots == 1)) continue;
                 P.cbatch = cbatch ? 1 : 0;
                 c_bytes = tma_out ? ng * cslots * (P.c_slot_bytes + P.p_slot_bytes) : 0;
@@ -658,7 +719,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     for (int i = 0; i < P.nprob; ++i) {
         const ConvDesc& d = descs[i];
         IgemmProblem& q = P.prob[i];
-        if (d.in.C != Cin || d.w->Cin != Cin || d.w->N != Ntot || d.in.H != H || d.in.W != W || d.in.B != d0.in.B ||
+        if (d.in.C != Cin || d.w->Cin != Cin || d.w->N != Ntot || (!cfix && (d.in.H != H || d.in.W != W)) || d.in.B != d0.in.B ||
             d.w->taps != d0.w->taps || (slab && d.dil != 1))
             return e.fail(AAU_ERR_INVALID, "grouped problems must share geometry");
         // activations: (C, W, H, B)
@@ -693,6 +754,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         q.outH = d.out.H; q.outW = d.out.W; q.out_ld = d.out.ld; q.out_choff = d.out.choff;
         q.convt_cout = d.convt_cout;
         q.gate_C = d.out.C; q.gate_plus_x = d.gate_plus_x;
+        q.fix_axis = d.fix_axis;
+        q.fix_coef = d.fix_coef;
+        q.fix_out = d.fix_axis == 0 ? d.out.H : d.out.W;
     }
     P.total_tiles = tile_begin;
     if (tma_out) {
@@ -730,6 +794,11 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     oi.kernel = "igemm_tc_kernel";
     for (const ConvDesc& d : descs) {
         const double px = (double)d.in.B * d.in.H * d.in.W;
+        if (d.epi == EPI_CONVTFIX) {                               // algorithmic work of ConvTranspose2d + resize, not of the padded GEMM
+            oi.flops += 2.0 * px * d.in.C * 4 * d.convt_cout;
+            oi.bytes += px * d.in.C * 2 + (double)d.in.C * 4 * d.convt_cout * 2 + (double)d.out.B * d.out.H * d.out.W * d.convt_cout * 2;
+            continue;
+        }
         oi.flops += 2.0 * px * d.w->K * d.w->N;
         oi.bytes += px * d.in.C * 2 + (double)d.w->K * d.w->N * 2;
         if (d.epi == EPI_STORE) oi.bytes += px * d.w->N * 2;
@@ -745,7 +814,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // not, the second half of the grid would simply run as a second wave over the same static tile striding.
     int grid = std::min(P.total_tiles, e.num_sms * ctas);
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
-    oi.name += " [" + std::string(rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap"))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
+    oi.name += " [" + std::string(cfix ? "tap2+fix" : (rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap")))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
                " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
@@ -961,13 +1030,34 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         const View gin = (l == 4) ? bo : dd[l + 1];
         const View gdst = sub_view(cat[l], ch[l], ch[l]);
         const bool fix = tmpg[l].p != nullptr;
-        {
+        // one-axis fix-up fused into the transposed conv when its [3*CC x 2*Cin] weight tile can stay in shared memory
+        const bool fixH = 2 * Hs[l + 1] != Hs[l], fixW = 2 * Ws[l + 1] != Ws[l];
+        int fcc = e.opt_fixcc > 0 ? e.opt_fixcc : 64;
+        while (fcc > 16 && ch[l] % fcc) fcc -= 16;
+        bool fused = false;
+        if (fix && fixH != fixW && e.opt_fusefix != 0 && e.opt_resident != 0 && ch[l] % fcc == 0 &&
+            (size_t)3 * fcc * 2 * (2 * ch[l]) * 2 <= 112 * 1024) {
+            const int axis = fixH ? 0 : 1;
+            std::vector<float> coef;
+            const GemmW* gwf = prep_upfix(e, l, axis, fcc);
+            if (gwf && fix_coefficients(axis == 0 ? 2 * Hs[l + 1] : 2 * Ws[l + 1], axis == 0 ? Hs[l] : Ws[l], coef)) {
+                float* dcoef = nullptr;
+                if (upload(e, coef, &dcoef) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "fix-up coefficient upload failed");
+                ConvDesc d;
+                d.w = gwf;
+                d.in = gin; d.out = gdst; d.epi = EPI_CONVTFIX; d.relu = 0; d.convt_cout = ch[l];
+                d.fix_axis = axis; d.fix_coef = dcoef; d.fix_cc = fcc;
+                if ((r = add_igemm(e, plan, p + ".up+resize", {d}, 0))) return r;
+                fused = true;
+            }
+        }
+        if (!fused) {
             ConvDesc d;
             d.w = &e.gw.at(p + ".up");
             d.in = gin; d.out = fix ? tmpg[l] : gdst; d.epi = EPI_CONVT; d.relu = 0; d.convt_cout = ch[l];
             if ((r = add_igemm(e, plan, p + ".up", {d}, 0))) return r;
         }
-        if (fix) {
+        if (fix && !fused) {
             const View in = tmpg[l];
             const long long items = (long long)B * Hs[l] * Ws[l] * (ch[l] / 8);
             const dim3 grid((unsigned)((Ws[l] * (ch[l] / 8) + 255) / 256), (unsigned)((Hs[l] + RESIZE_ROWS - 1) / RESIZE_ROWS), (unsigned)B);
@@ -1328,8 +1418,14 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         h->e.last_plan = nullptr;
         return AAU_OK;
     }
-    if (std::string(name) == "side" || std::string(name) == "pdl") {
-        (std::string(name) == "side" ? h->e.opt_side : h->e.opt_pdl) = value;
+    if (std::string(name) == "fixcc") {
+        h->e.opt_fixcc = value;
+        h->e.plans.clear();
+        h->e.last_plan = nullptr;
+        return AAU_OK;
+    }
+    if (std::string(name) == "side" || std::string(name) == "pdl" || std::string(name) == "fusefix") {
+        (std::string(name) == "side" ? h->e.opt_side : (std::string(name) == "pdl" ? h->e.opt_pdl : h->e.opt_fusefix)) = value;
         h->e.plans.clear();
         h->e.last_plan = nullptr;
         return AAU_OK;

@@ -46,6 +46,15 @@
 //                 directly inside concatenated buffers; ragged tiles are clipped by the TMA unit)
 //   EPI_CONVT   : ConvTranspose2d(2,2): column block (a,b) is TMA-stored through a strided view of the output whose
 //                 pixel (x, y) is output pixel (2x+b, 2y+a)
+//   EPI_CONVTFIX: ConvTranspose2d(2,2) fused with the decoder's one-row / one-column bilinear fix-up (F.interpolate to
+//                 the skip's size when the pooled size was odd: 2n -> 2n+1 along ONE axis).  The GEMM has two taps
+//                 along that axis (offset -1 and 0) and three column blocks per tile, up = X[j-1].W1, mid0 = X[j].W0,
+//                 mid1 = X[j].W1 (W0 / W1 = the transposed-conv phases along the fixed axis), i.e. the transposed-conv
+//                 rows 2j-1, 2j, 2j+1.  Output row o = 2j+p is a two-term blend of two ADJACENT transposed-conv rows,
+//                 so the epilogue forms both of its outputs as  c[o][0].up + c[o][1].mid0 + c[o][2].mid1 + bias  in
+//                 fp32 (c = ATen's bilinear weights, tabulated per output row on the host) and stores them through
+//                 the same strided (a,b) views as EPI_CONVT -- straight into the concatenated decoder buffer, with no
+//                 intermediate tensor, no separate resize kernel and a single rounding.
 //   EPI_GATE    : attention gate: psi = sigmoid(w_psi . relu(acc + bias) + b_psi); the skip tensor row is scaled
 //                 by psi (or 1+psi for the ablation flavour) in place; psi optionally written out
 //   EPI_OUTCONV : last decoder conv fused with out_conv: logit = w_out . relu(acc + bias) + b_out (fp32 out)
@@ -71,7 +80,7 @@
 
 namespace aau {
 
-enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3 };
+enum { EPI_STORE = 0, EPI_CONVT = 1, EPI_GATE = 2, EPI_OUTCONV = 3, EPI_CONVTFIX = 4 };
 enum { AMODE_TAP = 0, AMODE_SLAB = 1, AMODE_DXN = 2, AMODE_RS = 3 };
 enum { IGEMM_MAX_PROBLEMS = 4, IGEMM_MAX_SLOTS = 12, IGEMM_MAX_GROUPS = 4 };
 __host__ __device__ constexpr int igemm_threads(int ng) { return 64 + 128 * ng; }   // TMA warp + MMA warp + ng epilogue groups of 4 warps
@@ -108,7 +117,9 @@ struct alignas(64) IgemmProblem {
     int convt_cout;
     int gate_C, gate_plus_x;
     float scalar;           // GATE: b_psi; OUTCONV: b_out
-    int pad_;
+    int fix_axis;           // CONVTFIX: 0 = rows (H), 1 = columns (W)
+    int fix_out;            // CONVTFIX: output size along the fixed axis (2n + 1)
+    const float* fix_coef;  // CONVTFIX: [fix_out][3] blend weights on (up, mid0, mid1)
 };
 
 struct alignas(64) IgemmParams {
@@ -501,6 +512,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         const int ch = s - tap * q.nchunk;
                         int dy = 0, dx = 0;
                         if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
+                        else if (q.taps == 2) { dy = q.fix_axis == 0 ? tap - 1 : 0; dx = q.fix_axis == 1 ? tap - 1 : 0; }
                         ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (!res) ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (ptx::elect_one()) {
@@ -597,7 +609,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             const int n0 = (int)(blockIdx.x % q0.n_tiles) * P.n_out;
             float* sb0 = s_bias + (grp * 2) * (512 / NG);
             for (int i = etid; i < P.n_out; i += 128)
-                sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout : n0 + i));
+                sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout
+                                          : q0.epi == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
         }
         const uint32_t smem_c_u32 = ptx::smem_u32(smem_c), smem_p_u32 = ptx::smem_u32(smem_p);
         asm volatile("griddepcontrol.wait;" ::: "memory");          // before the first store / activation read of this role
@@ -625,7 +638,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             if (!bias_static) {
                 const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
                 for (int i = etid; i < P.n_out; i += 128)
-                    sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout : tc.n0 + i));
+                    sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout
+                                          : q.epi == EPI_CONVTFIX ? ((tc.n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q.convt_cout : tc.n0 + i));
             }
             TM_MARK(0);                                         // 0: tile bookkeeping
             if (etid == 0) WAIT_STORE_READS();                  // the store that last used the next staging tile has left smem
@@ -811,6 +825,66 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
               }
+            } else if (q.epi == EPI_CONVTFIX) {
+                // n tile = (phase t along the free axis, channel block); columns [up | mid0 | mid1], CC channels each
+                const int CC = P.BN / 3;
+                const int nt = tc.n0 / P.BN, nsub = q.convt_cout / CC;
+                const int t = nt / nsub, ch0 = (nt - t * nsub) * CC;
+                const int j = q.fix_axis == 0 ? y : x;                          // index along the fixed axis
+                float cf[2][3];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const int o = 2 * j + p;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cf[p][k] = o < q.fix_out ? __ldg(q.fix_coef + o * 3 + k) : 0.f;
+                }
+                const uint32_t row_base = (uint32_t)(srow * c_pitch);
+                const uint32_t xr = ((row_base >> 7) & swz_mask) << 4;
+                const uint32_t slot0 = smem_c_u32 + (uint32_t)(grp * P.cslots * P.c_slot_bytes);
+                for (int c0 = 0; c0 < CC; c0 += P.CB) {
+                    if (c0 > 0) {                                               // both staging tiles are reused per chunk
+                        if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        EPI_BAR();
+                    }
+                    for (int cc = 0; cc < P.CB; cc += 16) {
+                        uint32_t u[32], m0[32], m1[32];
+                        ptx::tmem_ld_32x16(taddr + c0 + cc, u);
+                        ptx::tmem_ld_32x16(taddr + CC + c0 + cc, m0);
+                        ptx::tmem_ld_32x16(taddr + 2 * CC + c0 + cc, m1);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                float f[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int c = v * 8 + i;
+                                    f[i] = fmaf(cf[p][0], __uint_as_float(u[c]), fmaf(cf[p][1], __uint_as_float(m0[c]),
+                                                fmaf(cf[p][2], __uint_as_float(m1[c]), sb[c0 + cc + c])));
+                                }
+                                const uint4 o4 = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
+                                sts128(slot0 + (uint32_t)(p * P.c_slot_bytes) + row_base + ((uint32_t)((cc + v * 8) * 2) ^ xr), o4);
+                            }
+                        }
+                    }
+                    if (c0 + P.CB >= CC) {                                      // accumulator fully read: free the TMEM stage
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    EPI_BAR();
+                    if (etid == 0) {
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const int ab = q.fix_axis == 0 ? p * 2 + t : t * 2 + p;   // (a, b) phase of the output view
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"((uint64_t)&P.tmC[ab]), "r"(slot0 + (uint32_t)(p * P.c_slot_bytes)), "r"(ch0 + c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
             } else {
                 // GATE / OUTCONV: dot = sum_n relu(acc_n + bias_n) * vec_n over all BN channels of the pixel
                 float dot = 0.f;

@@ -260,3 +260,26 @@ def test_planner_variants_agree(opts):
     assert (out - ref).abs().max().item() <= 0.03 * spread + 2e-2, f"{opts}: differs from the oracle"
     assert (out - base).abs().max().item() <= 0.03 * spread + 2e-2, f"{opts}: differs from the default plan"
     assert agreement(out, ref, 0.5) >= 0.995
+
+
+# ------------------------------------------------------------------------------------------------ fused up + fix-up
+@pytest.mark.parametrize("c,shape", [(32, (1, 146, 160)), (32, (2, 160, 146)), (16, (1, 82, 176)), (16, (2, 176, 90)), (48, (1, 146, 96))])
+def test_fused_transposed_conv_and_bilinear_fixup(c, shape):
+    """Odd size along ONE axis at some level: ConvTranspose2d + F.interpolate run as one GEMM with a blending epilogue
+    (EPI_CONVTFIX).  It must match the oracle at least as well as the two-kernel path it replaces."""
+    cfg = O.NetCfg(base_c=c)
+    sd, x = r1_case(cfg, shape, seed=9)
+    ref = O.forward(sd, x, cfg)
+    net = make_net(cfg, sd, "fp16")
+    fused = net(x.cuda()).cpu()
+    names = [r["layer"] for r in net.op_profile()]
+    assert any("up+resize" in n for n in names), f"no fused launch for {shape}: {names}"
+    net.set_option("fusefix", 0)
+    split = net(x.cuda()).cpu()
+    assert not any("up+resize" in r["layer"] for r in net.op_profile())
+    net.check_device()
+    spread = ref.std().item()
+    e_f, e_s = (fused - ref).abs(), (split - ref).abs()
+    assert e_f.max().item() <= 0.03 * spread + 2e-2
+    assert e_f.mean().item() <= 1.1 * e_s.mean().item() + 1e-5       # single rounding: never worse than convT -> store -> resize
+    assert agreement(fused, ref, 0.5) >= 0.995
