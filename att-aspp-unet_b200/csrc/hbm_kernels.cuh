@@ -17,19 +17,38 @@ __device__ __forceinline__ float load_px(const void* __restrict__ x, int x_dtype
     return x_dtype == 0 ? __ldg((const float*)x + idx) : (float)__ldg((const uint8_t*)x + idx) / 255.0f;
 }
 // Tile = STEM_TR rows x (256 / (C/8)) columns of one frame.  The (halo-padded, already normalised) input tile sits in
-// shared memory; a thread owns ONE column and ONE group of 8 output channels, keeps its 9x8 folded weights in
-// registers and walks down the rows with a sliding 3x3 window (3 shared-memory reads + 72 FMAs per pixel).  The
-// C/8 threads of a pixel write its C*2 bytes back to back and a warp covers 32/(C/8) neighbouring pixels, so every
-// store instruction writes whole contiguous 128-byte lines.  HBM-bound: 1 byte in, 2*C bytes out per pixel.
+// shared memory, every value duplicated into a float2 so that one LDS.64 yields the (v, v) operand of a packed FMA;
+// a thread owns ONE column and ONE group of 8 output channels, keeps its 9x8 folded weights in registers as 36
+// float pairs and walks down the rows with a sliding 3x3 window: per pixel 3 shared-memory reads and 36 FFMA2
+// (fma.rn.f32x2: two independent IEEE fp32 FMAs per instruction, sm_100) -- the kernel is bound by instruction
+// issue, not by its 1 byte in / 2*C bytes out per pixel of HBM traffic, so halving the FMA instructions is the lever.
+// The C/8 threads of a pixel write its C*2 bytes back to back and a warp covers 32/(C/8) neighbouring pixels, so
+// every store instruction writes whole contiguous 128-byte lines.
 // uint8 input is normalised through a 256-entry table of float(v)/255.0f (one IEEE division per thread per block).
 enum { STEM_TR = 16, STEM_MAX_TW = 128 };
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pair_f32(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 template <bool F16>
-__global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restrict__ x, int x_dtype, int B, int H, int W,
+__device__ __forceinline__ uint32_t pack_pair_relu(unsigned long long v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return pack2_relu<F16>(lo, hi);
+}
+template <bool F16>
+__global__ void __launch_bounds__(256, 2) stem_conv3x3_kernel(const void* __restrict__ x, int x_dtype, int B, int H, int W,
                                                            const float* __restrict__ w9c,   // [9][C], BN scale folded in
                                                            const float* __restrict__ bias,  // [C]
                                                            uint8_t* __restrict__ out, int out_ld, int out_choff, int C,
                                                            int tiles_x, int tiles_y) {
-    __shared__ float s_in[(STEM_TR + 2) * (STEM_MAX_TW + 2)];
+    __shared__ __align__(8) float2 s_in[(STEM_TR + 2) * (STEM_MAX_TW + 2)];
     __shared__ float s_lut[256];
     s_lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
     const int CG = C >> 3;                                        // 8-channel groups per pixel
@@ -37,56 +56,87 @@ __global__ void __launch_bounds__(256) stem_conv3x3_kernel(const void* __restric
     const int pitch = TWc + 2;
     const uint32_t pitch_mul = ((1u << 20) + pitch - 1) / pitch;  // i / pitch == (i * pitch_mul) >> 20 for i < 2^11
     const int cg = threadIdx.x % CG, col = threadIdx.x / CG;
-    float w[9][8], bz[8];
+    unsigned long long w2[9][4], bz2[4];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + t * C + cg * 8));
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(w9c + t * C + cg * 8 + 4));
-        w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b4.x; w[t][5] = b4.y; w[t][6] = b4.z; w[t][7] = b4.w;
+        w2[t][0] = pair_f32(a.x, a.y); w2[t][1] = pair_f32(a.z, a.w); w2[t][2] = pair_f32(b4.x, b4.y); w2[t][3] = pair_f32(b4.z, b4.w);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bz[i] = __ldg(bias + cg * 8 + i);
+    for (int i = 0; i < 4; ++i) bz2[i] = pair_f32(__ldg(bias + cg * 8 + 2 * i), __ldg(bias + cg * 8 + 2 * i + 1));
     const int per_img = tiles_x * tiles_y, ntiles = B * per_img;
+    const int n_in = (STEM_TR + 2) * pitch;                       // input pixels of a tile (with halo)
+    constexpr int FILL = ((STEM_TR + 2) * (STEM_MAX_TW + 2) + 255) / 256;   // input pixels per thread
+    // uint8 frames: the NEXT tile's input bytes are fetched into three registers while the current tile is being
+    // computed (a tile's fill was otherwise five dependent global-load latencies long); out-of-frame pixels are 0,
+    // which the table maps to 0.0f -- the zero padding of the convolution.
+    uint32_t raw[(FILL + 3) / 4];
+    auto fetch_u8 = [&](int tile) {
+#pragma unroll
+        for (int k = 0; k < (FILL + 3) / 4; ++k) raw[k] = 0;
+        if (tile >= ntiles) return;
+        const int b = tile / per_img, r0 = tile - b * per_img;
+        const int tyi = r0 / tiles_x, txi = r0 - tyi * tiles_x;
+        const int y0 = tyi * STEM_TR, x0 = txi * TWc;
+#pragma unroll
+        for (int k = 0; k < FILL; ++k) {
+            const int i = threadIdx.x + k * 256;
+            const int r = (int)(((uint32_t)i * pitch_mul) >> 20), cc = i - r * pitch;
+            const int yy = y0 + r - 1, xx = x0 + cc - 1;
+            if (i < n_in && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                raw[k >> 2] |= (uint32_t)__ldg((const uint8_t*)x + ((size_t)b * H + yy) * W + xx) << (8 * (k & 3));
+        }
+    };
+    if (x_dtype != 0) fetch_u8(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b = tile / per_img, r0 = tile - b * per_img;
         const int tyi = r0 / tiles_x, txi = r0 - tyi * tiles_x;
         const int y0 = tyi * STEM_TR, x0 = txi * TWc;
         __syncthreads();                                          // the previous tile has been consumed (and s_lut is written)
-        for (int i = threadIdx.x; i < (STEM_TR + 2) * pitch; i += 256) {
-            const int r = (int)(((uint32_t)i * pitch_mul) >> 20), cc = i - r * pitch;
-            const int yy = y0 + r - 1, xx = x0 + cc - 1;
-            float v = 0.f;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                const size_t idx = ((size_t)b * H + yy) * W + xx;
-                v = x_dtype == 0 ? __ldg((const float*)x + idx) : s_lut[__ldg((const uint8_t*)x + idx)];
+        if (x_dtype != 0) {
+#pragma unroll
+            for (int k = 0; k < FILL; ++k) {
+                const int i = threadIdx.x + k * 256;
+                if (i < n_in) {
+                    const float v = s_lut[(raw[k >> 2] >> (8 * (k & 3))) & 0xffu];
+                    s_in[i] = make_float2(v, v);
+                }
             }
-            s_in[i] = v;
+        } else {
+            for (int i = threadIdx.x; i < n_in; i += 256) {
+                const int r = (int)(((uint32_t)i * pitch_mul) >> 20), cc = i - r * pitch;
+                const int yy = y0 + r - 1, xx = x0 + cc - 1;
+                float v = 0.f;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg((const float*)x + ((size_t)b * H + yy) * W + xx);
+                s_in[i] = make_float2(v, v);
+            }
         }
+        if (x_dtype != 0) fetch_u8(tile + gridDim.x);             // in flight during the compute phase below
         __syncthreads();
         if (col < TWc && x0 + col < W) {
-            float v[3][3];
+            const unsigned long long* s2 = reinterpret_cast<const unsigned long long*>(s_in);
+            unsigned long long v[3][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { v[0][k] = s_in[col + k]; v[1][k] = s_in[pitch + col + k]; }
+            for (int k = 0; k < 3; ++k) { v[0][k] = s2[col + k]; v[1][k] = s2[pitch + col + k]; }
             uint8_t* dst = out + ((((size_t)b * H + y0) * W + x0 + col) * out_ld + out_choff + cg * 8) * 2;
             const size_t row_bytes = (size_t)W * out_ld * 2;
             const int nrow = min((int)STEM_TR, H - y0);
 #pragma unroll 3
             for (int r = 0; r < nrow; ++r) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v[2][k] = s_in[(r + 2) * pitch + col + k];
-                float a[8];
+                for (int k = 0; k < 3; ++k) v[2][k] = s2[(r + 2) * pitch + col + k];
+                unsigned long long a[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = bz[i];
+                for (int i = 0; i < 4; ++i) a[i] = bz2[i];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] = fmaf(v[ky][kx], w[ky * 3 + kx][i], a[i]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.f);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(a[0], a[1], F16), pack2(a[2], a[3], F16),
-                                                            pack2(a[4], a[5], F16), pack2(a[6], a[7], F16));
+                        for (int i = 0; i < 4; ++i) a[i] = ffma2(v[ky][kx], w2[ky * 3 + kx][i], a[i]);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_pair_relu<F16>(a[0]), pack_pair_relu<F16>(a[1]),
+                                                            pack_pair_relu<F16>(a[2]), pack_pair_relu<F16>(a[3]));
                 dst += row_bytes;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { v[0][k] = v[1][k]; v[1][k] = v[2][k]; }
