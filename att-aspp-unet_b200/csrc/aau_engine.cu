@@ -1334,6 +1334,38 @@ int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void
     return AAU_OK;
 }
 
+size_t aau_condition_workspace_bytes(const aau_handle* h, int N) {
+    return h && N > 0 ? (size_t)N * (2 * sizeof(int) + 64 * 256) + 512 : 0;       // {min, max} + 8x8 LUTs per frame
+}
+
+int aau_condition_frames(aau_handle* h, const uint8_t* frames, int N, int H, int W, uint8_t* out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!frames || !out || !workspace || N < 1 || H < 8 || W < 8) return e.fail(AAU_ERR_INVALID, "bad condition_frames arguments");
+    if (workspace_bytes < aau_condition_workspace_bytes(h, N)) return e.fail(AAU_ERR_WORKSPACE, "conditioning workspace too small");
+    if (frames == out) return e.fail(AAU_ERR_INVALID, "conditioning cannot run in place (3x3 median)");
+    cudaSetDevice(e.device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles = 8;                                             // cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8, 8))
+    const double clip_limit = 1.0;
+    // OpenCV pads BOTH axes (by a full tile where an axis already divides) as soon as one of them does not divide
+    const bool pad = (W % tiles) != 0 || (H % tiles) != 0;
+    const int Wp = pad ? W + tiles - W % tiles : W, Hp = pad ? H + tiles - H % tiles : H;
+    const int tw = Wp / tiles, th = Hp / tiles;
+    if (Hp - H > H - 1 || Wp - W > W - 1) return e.fail(AAU_ERR_INVALID, "frame too small for the 8x8 CLAHE grid");
+    const int clip = std::max((int)(clip_limit * (double)(tw * th) / 256.0), 1);
+    int* mm = (int*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint8_t* lut = (uint8_t*)(mm + 2 * (size_t)N);
+    minmax_init_kernel<<<(N + 255) / 256, 256, 0, s>>>(mm, N);
+    const int HW = H * W;
+    frame_minmax_kernel<<<dim3(std::max(1, std::min(32, HW / 4096)), N), 256, 0, s>>>(frames, HW, mm);
+    clahe_lut_kernel<<<dim3(tiles * tiles, N), 256, 0, s>>>(frames, H, W, mm, tiles, tiles, tw, th, clip, lut);
+    clahe_median_kernel<<<dim3((W + COND_TW - 1) / COND_TW, (H + COND_TH - 1) / COND_TH, N), 256, 0, s>>>(frames, H, W, mm, lut, tiles, tiles, tw, th, out);
+    AAU_CUDA(cudaGetLastError());
+    return AAU_OK;
+}
+
 int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream) {
     if (!h) return AAU_ERR_INVALID;
     Engine& e = h->e;

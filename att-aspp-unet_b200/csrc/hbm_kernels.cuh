@@ -426,3 +426,157 @@ __global__ void __launch_bounds__(1024) area_argmax_kernel(const int* __restrict
 }
 
 }  // namespace aau
+
+namespace aau {
+
+// ---------------------------------------------------------------------------------------------------------
+// Frame conditioning: what the reference does to every frame before the network,
+//   cv2.normalize(NORM_MINMAX, 0..255) -> uint8, cv2.createCLAHE(1.0, (8, 8)).apply, cv2.medianBlur(3)
+// (model_attention_aspp.py:11-17, inference.py:147-190), reproduced BIT-EXACTLY on uint8 frames: integer histogram
+// work plus the few fp32 operations OpenCV performs, in the same order and with the same roundings
+//   * normalize : saturate(rint(fmaf(v, (float)scale, (float)shift))), scale = 255 * (1 / (max - min)) in double
+//   * CLAHE LUT : per tile histogram over the REFLECT_101-padded frame, clip = max(int(clipLimit*area/256), 1), excess
+//                 redistributed (batch + strided residual), lut[i] = saturate(rint(cumsum[i] * (255.f / area)))
+//   * CLAHE blend: four LUT values, fp32 mul / add WITHOUT contraction, rint;  median: 3x3, replicated border.
+// HBM-bound byte work: three reads and one write of the sweep; the LUTs (16 KB per frame) stay in L2.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_minmax_kernel(const uint8_t* __restrict__ x, int HW, int* __restrict__ mm /* [N][2] = {min, max} */) {
+    const int frame = blockIdx.y;
+    const uint8_t* src = x + (size_t)frame * HW;
+    int lo = 255, hi = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int v = __ldg(src + i);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 2 * frame, lo);
+        atomicMax(mm + 2 * frame + 1, hi);
+    }
+}
+__global__ void minmax_init_kernel(int* mm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mm[2 * i] = 255; mm[2 * i + 1] = 0; }
+}
+
+struct NormCoef { float a, b; };
+__device__ __forceinline__ NormCoef norm_coef(const int* mm, int frame) {
+    const double smin = (double)mm[2 * frame], smax = (double)mm[2 * frame + 1];
+    const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+    NormCoef c;
+    c.a = (float)scale;
+    c.b = (float)(0.0 - smin * scale);
+    return c;
+}
+__device__ __forceinline__ int norm_u8(int v, NormCoef c) {
+    return min(255, max(0, __float2int_rn(__fmaf_rn((float)v, c.a, c.b))));
+}
+
+// grid = (tilesX * tilesY, N): one block builds the 256-entry LUT of one CLAHE tile
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ x, int H, int W, const int* __restrict__ mm,
+                                                        int tilesX, int tilesY, int tw, int th, int clip,
+                                                        uint8_t* __restrict__ lut /* [N][tilesY*tilesX][256] */) {
+    __shared__ int hist[256];
+    __shared__ int wsum[8];
+    __shared__ int s_clipped;
+    const int frame = blockIdx.y, tile = blockIdx.x;
+    const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const NormCoef nc = norm_coef(mm, frame);
+    hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_clipped = 0;
+    __syncthreads();
+    const uint8_t* src = x + (size_t)frame * H * W;
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int r = i / tw, c = i - r * tw;
+        int yy = ty * th + r, xx = tx * tw + c;                     // coordinates in the padded frame
+        if (yy >= H) yy = 2 * (H - 1) - yy;                         // BORDER_REFLECT_101
+        if (xx >= W) xx = 2 * (W - 1) - xx;
+        atomicAdd(&hist[norm_u8(__ldg(src + (size_t)yy * W + xx), nc)], 1);
+    }
+    __syncthreads();
+    int h = hist[threadIdx.x];
+    if (clip > 0) {
+        const int over = max(h - clip, 0);
+        int o = over;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) o += __shfl_xor_sync(0xffffffffu, o, s);
+        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&s_clipped, o);
+        __syncthreads();
+        const int clipped = s_clipped;
+        h = min(h, clip) + clipped / 256;
+        const int residual = clipped - (clipped / 256) * 256;
+        if (residual != 0) {
+            const int step = max(256 / residual, 1);
+            if (threadIdx.x % step == 0 && threadIdx.x / step < residual) ++h;
+        }
+    }
+    // inclusive prefix sum over the 256 bins
+    int s = h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    s += base;
+    const float lut_scale = 255.0f / (float)(tw * th);
+    lut[((size_t)frame * tilesX * tilesY + tile) * 256 + threadIdx.x] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn((float)s, lut_scale))));
+}
+
+__device__ __forceinline__ void sort2(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
+__device__ __forceinline__ int median9(int p0, int p1, int p2, int p3, int p4, int p5, int p6, int p7, int p8) {
+    sort2(p1, p2); sort2(p4, p5); sort2(p7, p8); sort2(p0, p1); sort2(p3, p4); sort2(p6, p7); sort2(p1, p2); sort2(p4, p5); sort2(p7, p8);
+    sort2(p0, p3); sort2(p5, p8); sort2(p4, p7); sort2(p3, p6); sort2(p1, p4); sort2(p2, p5); sort2(p4, p7); sort2(p4, p2); sort2(p6, p4);
+    sort2(p4, p2);
+    return p4;
+}
+
+// grid = (ceil(W/64), ceil(H/16), N): CLAHE-blended values of a 64x16 output tile plus a one-pixel (replicated) halo go
+// to shared memory, then every thread takes the 3x3 median of four pixels.
+enum { COND_TW = 64, COND_TH = 16 };
+__global__ void __launch_bounds__(256) clahe_median_kernel(const uint8_t* __restrict__ x, int H, int W, const int* __restrict__ mm,
+                                                           const uint8_t* __restrict__ lut, int tilesX, int tilesY, int tw, int th,
+                                                           uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_v[(COND_TH + 2) * (COND_TW + 2)];
+    const int frame = blockIdx.z, x0 = blockIdx.x * COND_TW, y0 = blockIdx.y * COND_TH;
+    const NormCoef nc = norm_coef(mm, frame);
+    const uint8_t* src = x + (size_t)frame * H * W;
+    const uint8_t* L = lut + (size_t)frame * tilesX * tilesY * 256;
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    for (int i = threadIdx.x; i < (COND_TH + 2) * (COND_TW + 2); i += 256) {
+        const int r = i / (COND_TW + 2), c = i - r * (COND_TW + 2);
+        const int yy = min(max(y0 + r - 1, 0), H - 1), xx = min(max(x0 + c - 1, 0), W - 1);   // BORDER_REPLICATE of the median
+        const int v = norm_u8(__ldg(src + (size_t)yy * W + xx), nc);
+        const float tyf = __fadd_rn(__fmul_rn((float)yy, inv_th), -0.5f), txf = __fadd_rn(__fmul_rn((float)xx, inv_tw), -0.5f);
+        int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
+        const float ya = __fadd_rn(tyf, -(float)ty1), xa = __fadd_rn(txf, -(float)tx1);
+        const float ya1 = __fadd_rn(1.0f, -ya), xa1 = __fadd_rn(1.0f, -xa);
+        const int ty2 = min(ty1 + 1, tilesY - 1), tx2 = min(tx1 + 1, tilesX - 1);
+        ty1 = max(ty1, 0); tx1 = max(tx1, 0);
+        const float l11 = (float)__ldg(L + (ty1 * tilesX + tx1) * 256 + v), l12 = (float)__ldg(L + (ty1 * tilesX + tx2) * 256 + v);
+        const float l21 = (float)__ldg(L + (ty2 * tilesX + tx1) * 256 + v), l22 = (float)__ldg(L + (ty2 * tilesX + tx2) * 256 + v);
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+        s_v[i] = (uint8_t)min(255, max(0, __float2int_rn(res)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COND_TH * COND_TW; i += 256) {
+        const int r = i / COND_TW, c = i - r * COND_TW;
+        const int y = y0 + r, xq = x0 + c;
+        if (y >= H || xq >= W) continue;
+        const uint8_t* p = s_v + r * (COND_TW + 2) + c;
+        out[((size_t)frame * H + y) * W + xq] =
+            (uint8_t)median9(p[0], p[1], p[2], p[COND_TW + 2], p[COND_TW + 3], p[COND_TW + 4], p[2 * (COND_TW + 2)], p[2 * (COND_TW + 2) + 1], p[2 * (COND_TW + 2) + 2]);
+    }
+}
+
+}  // namespace aau

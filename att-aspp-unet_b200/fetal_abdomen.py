@@ -158,14 +158,33 @@ class FetalAbdomenSegmentation:
         res = self.net(x, out=out)
         return res if isinstance(res, torch.Tensor) else res[0]
 
+    def condition_on_device(self, frames_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's per-frame conditioning (min-max stretch, CLAHE(1.0, 8x8), 3x3 median) on device uint8 frames
+        ``[n,H,W]``, bit exact with the OpenCV calls of model_attention_aspp.py:11-17 (``aau_condition_frames``).
+        The result is what ``preprocess_sweep`` returns times 255, and is fed to the network as uint8."""
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda and frames_u8.dim() == 3 and frames_u8.is_contiguous()
+        n, H, W = frames_u8.shape
+        if out is None:
+            out = torch.empty_like(frames_u8)
+        L, hnd = _capi.lib(), self.net.engine_handle()
+        need = L.aau_condition_workspace_bytes(hnd, n)
+        if getattr(self, "_cond_ws", None) is None or self._cond_ws.numel() < need:
+            self._cond_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        st = L.aau_condition_frames(hnd, frames_u8.data_ptr(), n, H, W, out.data_ptr(), self._cond_ws.data_ptr(), self._cond_ws.numel(),
+                                    torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(hnd, st, "aau_condition_frames")
+        return out
+
     @torch.no_grad()
     def segment_sweep(self, volume, frame_range: Optional[Tuple[int, int]] = None, prob_thr: Optional[float] = None,
-                      finalize: bool = True):
+                      finalize: bool = True, condition: bool = False):
         """Segment ``volume[frame_range]`` (``uint8`` or float ``[N,H,W]``, host numpy / pinned tensor) and select
         the best frame.  Returns a dict: ``areas`` (int32 numpy, this shard), ``best_idx`` (index into the full
         sweep, -1 if empty), ``best_area``, ``mask`` (uint8 [H,W], post-processed as the reference) and timing
         counters.  With ``finalize=False`` only ``areas`` are produced (multi-GPU shards: the caller gathers them,
-        picks the global frame with :func:`merge_shard_scores` and asks the owner rank for :meth:`frame_mask`)."""
+        picks the global frame with :func:`merge_shard_scores` and asks the owner rank for :meth:`frame_mask`).
+        ``condition=True`` (uint8 sweeps) runs the reference's frame conditioning on the device between the H2D copy
+        and the network, so a RAW sweep goes in."""
         thr = self.PROB_THRESHOLD if prob_thr is None else float(prob_thr)
         vol = torch.from_numpy(volume) if isinstance(volume, np.ndarray) else volume
         lo, hi = (0, vol.shape[0]) if frame_range is None else frame_range
@@ -220,6 +239,12 @@ class FetalAbdomenSegmentation:
             main.wait_event(ready[slot])
             x = self._staging[slot, :b]
             h2d += x.numel() * x.element_size()
+            if condition:
+                if not is_u8:
+                    raise ValueError("device-side conditioning takes uint8 sweeps (use preprocess_sweep on the host otherwise)")
+                if getattr(self, "_cond_out", None) is None or self._cond_out.shape != self._staging.shape[1:]:
+                    self._cond_out = torch.empty(self._staging.shape[1:], dtype=torch.uint8, device=dev)
+                x = self.condition_on_device(x, out=self._cond_out[:b])
             logits = self._net_logits(x, out=logits_all[s: s + b])
             consumed[slot].record(main)
             self._scores.run(logits[:, 0], _capi.AAU_IN_LOGITS, thr, areas[s: s + b], None, None)

@@ -91,8 +91,11 @@ def run(case_id: str | None = None, *, algorithm: FetalAbdomenSegmentation | Non
     sweep, _ = read_mha(paths[0])
     n_frames, ref_h, ref_w = sweep.shape
     if mode == "full":
-        conditioned = preprocess_sweep(sweep)
-        res = algorithm.segment_sweep(np.ascontiguousarray((conditioned * 255.0 + 0.5).astype(np.uint8)))
+        if sweep.dtype == np.uint8:                                 # raw sweep in, conditioning on the device (bit exact with OpenCV)
+            res = algorithm.segment_sweep(np.ascontiguousarray(sweep), condition=True)
+        else:                                                       # other voxel types: the reference's own host calls
+            conditioned = preprocess_sweep(sweep)
+            res = algorithm.segment_sweep(np.ascontiguousarray(np.rint(conditioned * 255.0).astype(np.uint8)))
         segmentation, frame_number = res["mask"], res["best_idx"]
     else:
         prob = algorithm.predict(paths, save_probabilities=bool(int(os.getenv("AAU_SAVE_PROB", "0"))))

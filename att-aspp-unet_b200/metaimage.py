@@ -72,7 +72,7 @@ def read_mha(path) -> Tuple[np.ndarray, Dict[str, str]]:
         raise MetaImageError(f"{path}: data block is shorter than DimSize says")
     arr = np.frombuffer(payload, dtype=dtype, count=count)
     shape = list(reversed(dims)) + ([channels] if channels > 1 else [])
-    return arr.reshape(shape).astype(dtype.newbyteorder("="), copy=False), header
+    return arr.reshape(shape).astype(dtype.newbyteorder("="), copy=True), header        # own, writable memory
 
 
 def write_mha(path, array: np.ndarray, spacing: Sequence[float] = (1.0, 1.0, 1.0), compress: bool = True,

@@ -114,6 +114,16 @@ int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, vo
  * model_attention_aspp.py:54 for callers that want the probability volume itself (`predict`).  Asynchronous. */
 int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void* stream);
 
+/* Frame conditioning of the reference wrapper on the device, bit exact with the OpenCV calls it makes
+ * (model_attention_aspp.py:11-17, inference.py:147-190): per frame `cv2.normalize(NORM_MINMAX, 0, 255)` -> uint8,
+ * `cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8,8)).apply`, `cv2.medianBlur(3)`.
+ *   frames : device uint8 [N,H,W];  out : device uint8 [N,H,W] (not in place), to be fed to aau_forward as AAU_X_U8
+ *            (which applies the reference's `/ 255.0`)
+ *   workspace : device scratch of aau_condition_workspace_bytes(h, N) bytes.  Asynchronous on `stream`. */
+size_t aau_condition_workspace_bytes(const aau_handle* h, int N);
+int aau_condition_frames(aau_handle* h, const uint8_t* frames, int N, int H, int W, uint8_t* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
  * the device. */
 int aau_device_fault(aau_handle* h);

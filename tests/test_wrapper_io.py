@@ -176,3 +176,26 @@ def test_engine_predict_and_run_match_reference(gold, case, tmp_path):
     vol, _ = metaimage.read_mha(tmp_path / "out_full/images/fetal-abdomen-segmentation/caseF.mha")
     fr = json.loads((tmp_path / "out_full/fetal-abdomen-frame-number.json").read_text())
     assert vol.shape == sweep.shape and -1 <= fr < sweep.shape[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 562, 744), (3, 250, 330), (4, 301, 333), (2, 64, 64), (2, 120, 97)])
+def test_device_conditioning_is_bit_exact_with_opencv(shape):
+    """aau_condition_frames (min-max, CLAHE 1.0 / 8x8, median 3) against the oracle's cv2 calls -- the same calls the
+    reference makes (pinned by the reference-run golden above) -- on speckle, random, constant and narrow-range frames."""
+    from attention_aspp_unet import AttentionASPPUNet
+    from fetal_abdomen import FetalAbdomenSegmentation
+    n, h, w = shape
+    rng = np.random.default_rng(n * h + w)
+    sweep = O.synthetic_sweep(n, h, w, seed=h, peak=n // 2)
+    sweep[1] = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if n > 2:
+        sweep[2] = (rng.random((h, w)) ** 3 * 180 + 17).astype(np.uint8)          # narrow range: the min-max stretch matters
+    if n > 3:
+        sweep[3] = 77                                                              # constant frame: scale 0
+    want = np.rint(O.condition_frames(sweep) * 255).astype(np.uint8)
+    algo = FetalAbdomenSegmentation(net=AttentionASPPUNet(base_c=16), batch=4)
+    got = algo.condition_on_device(torch.from_numpy(sweep).cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    bad = int((got != want).sum())
+    assert bad == 0, f"{bad} of {got.size} conditioned pixels differ from OpenCV (max |d| {np.abs(got.astype(int) - want.astype(int)).max()})"
