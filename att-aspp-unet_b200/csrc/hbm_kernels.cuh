@@ -443,11 +443,21 @@ namespace aau {
 __global__ void __launch_bounds__(256) frame_minmax_kernel(const uint8_t* __restrict__ x, int HW, int* __restrict__ mm /* [N][2] = {min, max} */) {
     const int frame = blockIdx.y;
     const uint8_t* src = x + (size_t)frame * HW;
-    int lo = 255, hi = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        const int v = __ldg(src + i);
-        lo = min(lo, v);
-        hi = max(hi, v);
+    uint32_t lo4 = 0xffffffffu, hi4 = 0u;                          // four byte lanes each (SIMD-in-word min / max)
+    const int head = (int)((16 - ((uintptr_t)src & 15)) & 15);     // bytes before the first 16-byte boundary
+    const int n16 = HW > head ? (HW - head) >> 4 : 0;
+    const uint4* v16 = reinterpret_cast<const uint4*>(src + head);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(v16 + i);
+        lo4 = __vminu4(__vminu4(lo4, v.x), __vminu4(v.y, __vminu4(v.z, v.w)));
+        hi4 = __vmaxu4(__vmaxu4(hi4, v.x), __vmaxu4(v.y, __vmaxu4(v.z, v.w)));
+    }
+    int lo = min(min(lo4 & 255, (lo4 >> 8) & 255), min((lo4 >> 16) & 255, lo4 >> 24));
+    int hi = max(max(hi4 & 255, (hi4 >> 8) & 255), max((hi4 >> 16) & 255, hi4 >> 24));
+    if (blockIdx.x == 0) {                                          // unaligned head and tail bytes
+        const int tail0 = head + n16 * 16;
+        for (int i = threadIdx.x; i < min(head, HW); i += blockDim.x) { const int v = __ldg(src + i); lo = min(lo, v); hi = max(hi, v); }
+        for (int i = tail0 + threadIdx.x; i < HW; i += blockDim.x) { const int v = __ldg(src + i); lo = min(lo, v); hi = max(hi, v); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -477,35 +487,44 @@ __device__ __forceinline__ int norm_u8(int v, NormCoef c) {
     return min(255, max(0, __float2int_rn(__fmaf_rn((float)v, c.a, c.b))));
 }
 
-// grid = (tilesX * tilesY, N): one block builds the 256-entry LUT of one CLAHE tile
+// grid = (tilesX * tilesY, N): one block builds the 256-entry LUT of one CLAHE tile.  Every warp counts into its own
+// 256-bin histogram (speckle frames put most pixels into a few bins: shared-memory atomics of one warp serialise on
+// those, eight private copies divide the contention) and walks whole tile rows, so there is no per-pixel division.
 __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ x, int H, int W, const int* __restrict__ mm,
                                                         int tilesX, int tilesY, int tw, int th, int clip,
                                                         uint8_t* __restrict__ lut /* [N][tilesY*tilesX][256] */) {
-    __shared__ int hist[256];
+    __shared__ int whist[8][256];
     __shared__ int wsum[8];
     __shared__ int s_clipped;
     const int frame = blockIdx.y, tile = blockIdx.x;
     const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const NormCoef nc = norm_coef(mm, frame);
-    hist[threadIdx.x] = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) whist[w][threadIdx.x] = 0;
     if (threadIdx.x == 0) s_clipped = 0;
     __syncthreads();
     const uint8_t* src = x + (size_t)frame * H * W;
-    for (int i = threadIdx.x; i < tw * th; i += 256) {
-        const int r = i / tw, c = i - r * tw;
-        int yy = ty * th + r, xx = tx * tw + c;                     // coordinates in the padded frame
+    for (int r = warp; r < th; r += 8) {
+        int yy = ty * th + r;                                       // row in the padded frame
         if (yy >= H) yy = 2 * (H - 1) - yy;                         // BORDER_REFLECT_101
-        if (xx >= W) xx = 2 * (W - 1) - xx;
-        atomicAdd(&hist[norm_u8(__ldg(src + (size_t)yy * W + xx), nc)], 1);
+        const uint8_t* row = src + (size_t)yy * W;
+        for (int c = lane; c < tw; c += 32) {
+            int xx = tx * tw + c;
+            if (xx >= W) xx = 2 * (W - 1) - xx;
+            atomicAdd(&whist[warp][norm_u8(__ldg(row + xx), nc)], 1);
+        }
     }
     __syncthreads();
-    int h = hist[threadIdx.x];
+    int h = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) h += whist[w][threadIdx.x];
     if (clip > 0) {
         const int over = max(h - clip, 0);
         int o = over;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) o += __shfl_xor_sync(0xffffffffu, o, s);
-        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&s_clipped, o);
+        if (lane == 0 && o) atomicAdd(&s_clipped, o);
         __syncthreads();
         const int clipped = s_clipped;
         h = min(h, clip) + clipped / 256;
@@ -517,7 +536,6 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     }
     // inclusive prefix sum over the 256 bins
     int s = h;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, s, o);
@@ -532,50 +550,92 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     lut[((size_t)frame * tilesX * tilesY + tile) * 256 + threadIdx.x] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn((float)s, lut_scale))));
 }
 
-__device__ __forceinline__ void sort2(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
-__device__ __forceinline__ int median9(int p0, int p1, int p2, int p3, int p4, int p5, int p6, int p7, int p8) {
-    sort2(p1, p2); sort2(p4, p5); sort2(p7, p8); sort2(p0, p1); sort2(p3, p4); sort2(p6, p7); sort2(p1, p2); sort2(p4, p5); sort2(p7, p8);
-    sort2(p0, p3); sort2(p5, p8); sort2(p4, p7); sort2(p3, p6); sort2(p1, p4); sort2(p2, p5); sort2(p4, p7); sort2(p4, p2); sort2(p6, p4);
-    sort2(p4, p2);
+// four pixels per 32-bit word: compare-exchange of byte lanes
+__device__ __forceinline__ void sort2x4(uint32_t& a, uint32_t& b) { const uint32_t t = __vminu4(a, b); b = __vmaxu4(a, b); a = t; }
+__device__ __forceinline__ uint32_t median9x4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t p5, uint32_t p6,
+                                              uint32_t p7, uint32_t p8) {      // 19-exchange median-of-9 network, byte-wise
+    sort2x4(p1, p2); sort2x4(p4, p5); sort2x4(p7, p8); sort2x4(p0, p1); sort2x4(p3, p4); sort2x4(p6, p7);
+    sort2x4(p1, p2); sort2x4(p4, p5); sort2x4(p7, p8); sort2x4(p0, p3); sort2x4(p5, p8); sort2x4(p4, p7);
+    sort2x4(p3, p6); sort2x4(p1, p4); sort2x4(p2, p5); sort2x4(p4, p7); sort2x4(p4, p2); sort2x4(p6, p4);
+    sort2x4(p4, p2);
     return p4;
 }
 
-// grid = (ceil(W/64), ceil(H/16), N): CLAHE-blended values of a 64x16 output tile plus a one-pixel (replicated) halo go
-// to shared memory, then every thread takes the 3x3 median of four pixels.
-enum { COND_TW = 64, COND_TH = 16 };
+// grid = (ceil(W/COND_TW), ceil(H/COND_TH), N).  Phase 1: the CLAHE-blended values of a COND_TW x COND_TH output tile
+// plus a replicated one-pixel halo go to shared memory (row stride padded to words); the interpolation indices and
+// weights of the tile's rows / columns are tabulated once per block.  Phase 2: a thread takes the 3x3 medians of FOUR
+// horizontally adjacent pixels at once with byte-lane min / max (the unaligned 3x3 window words come from two aligned
+// shared-memory words and a funnel shift) and writes one 32-bit word.
+enum { COND_TW = 128, COND_TH = 16, COND_PITCH = COND_TW + 8 };     // halo column at byte 3 of each row, data from byte 4
 __global__ void __launch_bounds__(256) clahe_median_kernel(const uint8_t* __restrict__ x, int H, int W, const int* __restrict__ mm,
                                                            const uint8_t* __restrict__ lut, int tilesX, int tilesY, int tw, int th,
                                                            uint8_t* __restrict__ out) {
-    __shared__ uint8_t s_v[(COND_TH + 2) * (COND_TW + 2)];
+    __shared__ __align__(16) uint8_t s_v[(COND_TH + 2) * COND_PITCH];
+    __shared__ int s_i1[COND_TW + 2 + COND_TH + 2], s_i2[COND_TW + 2 + COND_TH + 2], s_src[COND_TW + 2 + COND_TH + 2];
+    __shared__ float s_a[COND_TW + 2 + COND_TH + 2];
     const int frame = blockIdx.z, x0 = blockIdx.x * COND_TW, y0 = blockIdx.y * COND_TH;
     const NormCoef nc = norm_coef(mm, frame);
     const uint8_t* src = x + (size_t)frame * H * W;
     const uint8_t* L = lut + (size_t)frame * tilesX * tilesY * 256;
-    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
-    for (int i = threadIdx.x; i < (COND_TH + 2) * (COND_TW + 2); i += 256) {
-        const int r = i / (COND_TW + 2), c = i - r * (COND_TW + 2);
-        const int yy = min(max(y0 + r - 1, 0), H - 1), xx = min(max(x0 + c - 1, 0), W - 1);   // BORDER_REPLICATE of the median
-        const int v = norm_u8(__ldg(src + (size_t)yy * W + xx), nc);
-        const float tyf = __fadd_rn(__fmul_rn((float)yy, inv_th), -0.5f), txf = __fadd_rn(__fmul_rn((float)xx, inv_tw), -0.5f);
-        int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
-        const float ya = __fadd_rn(tyf, -(float)ty1), xa = __fadd_rn(txf, -(float)tx1);
-        const float ya1 = __fadd_rn(1.0f, -ya), xa1 = __fadd_rn(1.0f, -xa);
-        const int ty2 = min(ty1 + 1, tilesY - 1), tx2 = min(tx1 + 1, tilesX - 1);
-        ty1 = max(ty1, 0); tx1 = max(tx1, 0);
-        const float l11 = (float)__ldg(L + (ty1 * tilesX + tx1) * 256 + v), l12 = (float)__ldg(L + (ty1 * tilesX + tx2) * 256 + v);
-        const float l21 = (float)__ldg(L + (ty2 * tilesX + tx1) * 256 + v), l22 = (float)__ldg(L + (ty2 * tilesX + tx2) * 256 + v);
-        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-        s_v[i] = (uint8_t)min(255, max(0, __float2int_rn(res)));
+    // per-column (first COND_TW + 2 entries) and per-row (the rest) source coordinate, LUT plane offsets and weight
+    for (int i = threadIdx.x; i < COND_TW + 2 + COND_TH + 2; i += 256) {
+        const bool is_col = i < COND_TW + 2;
+        const int k = is_col ? i : i - (COND_TW + 2);
+        const int lim = is_col ? W : H, tsz = is_col ? tw : th, ntile = is_col ? tilesX : tilesY;
+        const int p = min(max((is_col ? x0 : y0) + k - 1, 0), lim - 1);                 // BORDER_REPLICATE of the median
+        const float tf = __fadd_rn(__fmul_rn((float)p, 1.0f / (float)tsz), -0.5f);
+        const int t1 = (int)floorf(tf);
+        s_a[i] = __fadd_rn(tf, -(float)t1);
+        s_i1[i] = max(t1, 0) * (is_col ? 256 : tilesX * 256);
+        s_i2[i] = min(t1 + 1, ntile - 1) * (is_col ? 256 : tilesX * 256);
+        s_src[i] = p;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < COND_TH * COND_TW; i += 256) {
-        const int r = i / COND_TW, c = i - r * COND_TW;
-        const int y = y0 + r, xq = x0 + c;
+    // a thread owns one column (its interpolation parameters live in registers) and walks every second row; the two
+    // halo columns are done by the first 2 x (COND_TH + 2) threads afterwards
+    auto blend = [&](int c, int r, int srcx, int i1c, int i2c, float xa, float xa1) {
+        const int ri = COND_TW + 2 + r;
+        const int v = norm_u8(__ldg(src + (size_t)s_src[ri] * W + srcx), nc);
+        const float ya = s_a[ri], ya1 = __fadd_rn(1.0f, -ya);
+        const uint8_t* L1 = L + v + s_i1[ri];
+        const uint8_t* L2 = L + v + s_i2[ri];
+        const float l11 = (float)__ldg(L1 + i1c), l12 = (float)__ldg(L1 + i2c), l21 = (float)__ldg(L2 + i1c), l22 = (float)__ldg(L2 + i2c);
+        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa)), bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+        s_v[r * COND_PITCH + 3 + c] = (uint8_t)min(255, max(0, __float2int_rn(res)));
+    };
+    {
+        const int c = 1 + (threadIdx.x & (COND_TW - 1));
+        const int srcx = s_src[c], i1c = s_i1[c], i2c = s_i2[c];
+        const float xa = s_a[c], xa1 = __fadd_rn(1.0f, -xa);
+        for (int r = threadIdx.x / COND_TW; r < COND_TH + 2; r += 256 / COND_TW) blend(c, r, srcx, i1c, i2c, xa, xa1);
+    }
+    if (threadIdx.x < 2 * (COND_TH + 2)) {
+        const int c = threadIdx.x < COND_TH + 2 ? 0 : COND_TW + 1, r = threadIdx.x < COND_TH + 2 ? threadIdx.x : threadIdx.x - (COND_TH + 2);
+        blend(c, r, s_src[c], s_i1[c], s_i2[c], s_a[c], __fadd_rn(1.0f, -s_a[c]));
+    }
+    __syncthreads();
+    const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_v);
+    for (int i = threadIdx.x; i < COND_TH * (COND_TW / 4); i += 256) {
+        const int r = i / (COND_TW / 4), q = i - r * (COND_TW / 4);                    // output row, word (4 pixels) in the row
+        const int y = y0 + r, xq = x0 + 4 * q;
         if (y >= H || xq >= W) continue;
-        const uint8_t* p = s_v + r * (COND_TW + 2) + c;
-        out[((size_t)frame * H + y) * W + xq] =
-            (uint8_t)median9(p[0], p[1], p[2], p[COND_TW + 2], p[COND_TW + 3], p[COND_TW + 4], p[2 * (COND_TW + 2)], p[2 * (COND_TW + 2) + 1], p[2 * (COND_TW + 2) + 2]);
+        uint32_t p[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t* row = s_w + ((r + k) * COND_PITCH >> 2) + q;                // word q holds bytes 4q..4q+3; pixel columns start at byte 4
+            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+            p[3 * k + 0] = __funnelshift_r(w0, w1, 24);                                 // columns 4q-1 .. 4q+2
+            p[3 * k + 1] = w1;                                                          // columns 4q   .. 4q+3
+            p[3 * k + 2] = __funnelshift_r(w1, w2, 8);                                  // columns 4q+1 .. 4q+4
+        }
+        const uint32_t m = median9x4(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+        uint8_t* dst = out + ((size_t)frame * H + y) * W + xq;
+        if (xq + 3 < W && (((uintptr_t)dst) & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(dst) = m;
+        } else {
+            for (int k = 0; k < 4 && xq + k < W; ++k) dst[k] = (uint8_t)(m >> (8 * k));
+        }
     }
 }
 
