@@ -1366,6 +1366,30 @@ int aau_condition_frames(aau_handle* h, const uint8_t* frames, int N, int H, int
     return AAU_OK;
 }
 
+int aau_flip_w(aau_handle* h, const void* x, int x_dtype, int64_t rows, int W, void* y, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!x || !y || x == y || rows < 1 || W < 1) return e.fail(AAU_ERR_INVALID, "bad flip_w arguments");
+    if (x_dtype != AAU_X_F32 && x_dtype != AAU_X_U8) return e.fail(AAU_ERR_INVALID, "unknown x_dtype");
+    cudaSetDevice(e.device);
+    const int grid = (int)std::min<long long>(((long long)rows * W + 255) / 256, (long long)e.num_sms * 16);
+    if (x_dtype == AAU_X_U8) flip_w_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, (long long)rows, W, (uint8_t*)y);
+    else                     flip_w_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (long long)rows, W, (float*)y);
+    AAU_CUDA(cudaGetLastError());
+    return AAU_OK;
+}
+
+int aau_tta_prob(aau_handle* h, const float* logits, const float* logits_of_flipped, int64_t rows, int W, float* prob, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!logits || !logits_of_flipped || !prob || rows < 1 || W < 1) return e.fail(AAU_ERR_INVALID, "bad tta_prob arguments");
+    cudaSetDevice(e.device);
+    const int grid = (int)std::min<long long>(((long long)rows * W + 255) / 256, (long long)e.num_sms * 16);
+    tta_prob_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, logits_of_flipped, (long long)rows, W, prob);
+    AAU_CUDA(cudaGetLastError());
+    return AAU_OK;
+}
+
 int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream) {
     if (!h) return AAU_ERR_INVALID;
     Engine& e = h->e;

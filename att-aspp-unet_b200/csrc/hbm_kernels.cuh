@@ -639,4 +639,29 @@ __global__ void __launch_bounds__(256) clahe_median_kernel(const uint8_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Flip test-time augmentation of the pipeline CLI (attention_aspp_unet_pipeline_stage.py:336-338, test_ablation.py:365-371):
+//   prob = sigmoid((net(x) + flip(net(flip(x, W)), W)) / 2)
+// `flip_w_kernel` mirrors frames along W (uint8 or fp32 elements), `tta_prob_kernel` averages the logits of the plain
+// and the mirrored pass (reading the second one mirrored back) and applies the sigmoid, all in fp32.
+template <typename T>
+__global__ void __launch_bounds__(256) flip_w_kernel(const T* __restrict__ x, long long rows, int W, T* __restrict__ y) {
+    const long long total = rows * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / W;
+        const int c = (int)(i - r * W);
+        y[i] = __ldg(x + r * W + (W - 1 - c));
+    }
+}
+__global__ void __launch_bounds__(256) tta_prob_kernel(const float* __restrict__ l, const float* __restrict__ lf, long long rows, int W,
+                                                       float* __restrict__ prob) {
+    const long long total = rows * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / W;
+        const int c = (int)(i - r * W);
+        const float m = __fmul_rn(__fadd_rn(__ldg(l + i), __ldg(lf + r * W + (W - 1 - c))), 0.5f);
+        prob[i] = 1.f / (1.f + expf(-m));
+    }
+}
+
 }  // namespace aau

@@ -114,6 +114,13 @@ int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, vo
  * model_attention_aspp.py:54 for callers that want the probability volume itself (`predict`).  Asynchronous. */
 int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void* stream);
 
+/* Flip test-time augmentation of the pipeline CLI (attention_aspp_unet_pipeline_stage.py:336-338, test_ablation.py:365-371):
+ * `sigmoid((net(x) + flip(net(flip(x, [-1])), [-1])) / 2)`.  aau_flip_w mirrors `rows` rows of W elements (uint8 or fp32,
+ * x_dtype as in aau_forward; not in place); aau_tta_prob combines the logits of the plain pass with those of the mirrored
+ * pass (read mirrored back) into probabilities.  Device pointers, asynchronous on `stream`. */
+int aau_flip_w(aau_handle* h, const void* x, int x_dtype, int64_t rows, int W, void* y, void* stream);
+int aau_tta_prob(aau_handle* h, const float* logits, const float* logits_of_flipped, int64_t rows, int W, float* prob, void* stream);
+
 /* Frame conditioning of the reference wrapper on the device, bit exact with the OpenCV calls it makes
  * (model_attention_aspp.py:11-17, inference.py:147-190): per frame `cv2.normalize(NORM_MINMAX, 0, 255)` -> uint8,
  * `cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8,8)).apply`, `cv2.medianBlur(3)`.

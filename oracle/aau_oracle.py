@@ -31,6 +31,9 @@ Reference lines restated (all paths relative to /root/reference):
   crop_roi_224         model_attention_aspp.py:20-30
   FetalAbdomenSegmentation.predict (sample 128, ROI, batch 8, paste back)   model_attention_aspp.py:41-65
   write_array_as_image_file (volume semantics)    inference.py:208-254
+  refine_mask / _circularity_score / select_best  test_ablation.py:373-403 (pipeline twin :340-353; its select_best is broken)
+  measure_ac_mm / _ellipse_circum                 attention_aspp_unet_pipeline_stage.py:355-374
+  pipeline slice loop (resize 512, TTA, resize back, blur, threshold, refine)   attention_aspp_unet_pipeline_stage.py:486-501
 """
 from __future__ import annotations
 
@@ -420,6 +423,86 @@ def output_volume(mask_2d: np.ndarray, frame_number: int, number_of_frames: int)
     the frame, then `> 0.5 -> 1`."""
     vol = convert_2d_mask_to_3d(np.squeeze(mask_2d).astype(np.float32), frame_number, number_of_frames)
     return np.where(vol > 0.5, 1, 0).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+# pipeline CLI recipe (SURVEY.md section 8 f2 / f4)
+# --------------------------------------------------------------------------------------------
+def label8(m: np.ndarray) -> np.ndarray:
+    """skimage.measure.label(m) for a 2-D array: full (8-) connectivity.  skimage is absent; scipy's labelling with a 3x3
+    structure yields the same partition (label numbering may differ, the callers only use component membership / sizes)."""
+    import scipy.ndimage as ndi
+    return ndi.label(m, structure=np.ones((3, 3), np.uint8))[0]
+
+
+def refine_mask(m: np.ndarray) -> np.ndarray:
+    """test_ablation.py:373-387."""
+    import cv2
+    from scipy.ndimage import binary_fill_holes
+    if m.sum() == 0:
+        return m
+    lab = label8(m)
+    cnt = np.bincount(lab.ravel())
+    cnt[0] = 0
+    keep = [i for i, c in enumerate(cnt) if c >= max(20, int(0.0015 * m.size))]
+    if not keep:
+        return np.zeros_like(m)
+    m = (np.isin(lab, keep)).astype(np.uint8)
+    lab2 = label8(m)
+    bc = np.bincount(lab2.ravel())
+    bc[0] = 0
+    m = (lab2 == np.argmax(bc)).astype(np.uint8)
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (7, 7))
+    return binary_fill_holes(cv2.morphologyEx(m, cv2.MORPH_CLOSE, k)).astype(np.uint8)
+
+
+def circularity_score(mask: np.ndarray) -> float:
+    """test_ablation.py:389-396."""
+    import cv2
+    cnts, _ = cv2.findContours(mask.astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    if not cnts:
+        return 0.0
+    c = max(cnts, key=cv2.contourArea)
+    area = cv2.contourArea(c)
+    peri = cv2.arcLength(c, True)
+    return 0.0 if peri <= 1e-6 else 4 * np.pi * area / (peri ** 2)
+
+
+def select_best(stack, topk: int = 5) -> int:
+    """test_ablation.py:398-403."""
+    if len(stack) == 0:
+        return 0
+    areas = np.array([(m > 0).sum() for m in stack])
+    idx = areas.argsort()[::-1][: max(1, min(topk, len(areas)))]
+    return int(max(idx, key=lambda i: circularity_score(stack[i])))
+
+
+def measure_ac_mm(mask01: np.ndarray, spacing) -> float:
+    """attention_aspp_unet_pipeline_stage.py:355-374."""
+    import cv2
+    import math
+    cnts, _ = cv2.findContours(mask01.astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    if not cnts:
+        return 0.0
+    c = max(cnts, key=cv2.contourArea)
+    if len(c) >= 5:
+        (_, _), (MA, ma), _ = cv2.fitEllipse(c)
+        a, b = MA / 2 * spacing[0], ma / 2 * spacing[1]
+        h = ((a - b) ** 2) / ((a + b) ** 2)
+        return math.pi * (a + b) * (1 + 3 * h / (10 + math.sqrt(4 - 3 * h)))
+    return cv2.arcLength(c, True) * float(sum(spacing) / 2)
+
+
+def pipeline_slice_prob(sd, frame_u8: np.ndarray, cfg: NetCfg = NetCfg(), img_size: int = 512) -> np.ndarray:
+    """One slice of the CLI loop up to the blurred probability map (attention_aspp_unet_pipeline_stage.py:487-497):
+    condition, Resize(512) (albumentations -> cv2.resize, INTER_LINEAR), ToFloat(255), flip TTA, resize back, blur."""
+    import cv2
+    e = np.rint(condition_frames(frame_u8[None])[0] * 255).astype(np.uint8)
+    x = torch.from_numpy(cv2.resize(e, (img_size, img_size), interpolation=cv2.INTER_LINEAR).astype(np.float32) / 255.0)[None, None]
+    with torch.no_grad():
+        prob = predict_prob_tta(sd, x, cfg)[0, 0].numpy()
+    prob = cv2.resize(prob, frame_u8.shape[::-1])
+    return cv2.GaussianBlur(prob, (5, 5), 0)
 
 
 # --------------------------------------------------------------------------------------------
