@@ -610,6 +610,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     bool rs = conv3 && d0.dil == 1 && descs.size() == 1 && Ntot == BN && BN <= 64 && Cin <= Ntot && e.opt_rs != 0 &&
               (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 3) && e.opt_resident != 0 &&
               (size_t)9 * Cin * BN * 2 <= 112 * 1024;
+    // measured A/B (B200, batch 28): with fused pooling and weights too large for two CTAs per SM (d2.1, 64 -> 64) the
+    // dx-stacked form is 7 % faster; everywhere else row-shifted taps win or tie
+    if (rs && dxn && want_pool && (size_t)9 * Cin * BN * 2 > 64 * 1024 && e.opt_amode < 0) rs = false;
     if (rs) { dxn = false; n_out = BN; }
     if (dxn || rs) slab = true;                                    // shares the slab geometry code below
     P.amode = rs ? AMODE_RS : (dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP));
