@@ -1457,49 +1457,31 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
     return AAU_OK;
 }
 
+// Planner / measurement switches (tests force every staging variant through these; bench.py --opt name=value):
+//   amode (-1 auto, 0 tap, 1 slab, 2 dx-stacked, 3 row-shifted), rs, rs_mt (0 rule / 1 never / 2 always), resident, ctas,
+//   ng (0 auto / 2 / 4 epilogue groups), cslots, mt, slab_max_bn, fusepool, fusefix, fixcc, side, pdl, titer, profile
 int aau_set_option(aau_handle* h, const char* name, int value) {
     if (!h || !name) return AAU_ERR_INVALID;
-    if (std::string(name) == "amode") {
-        h->e.opt_amode = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
+    Engine& e = h->e;
+    const std::string n(name);
+    if (n == "profile") {                                            // does not change the plans
+        e.opt_profile = value;
         return AAU_OK;
     }
-    if (std::string(name) == "resident" || std::string(name) == "ctas" || std::string(name) == "fusepool") {
-        (std::string(name) == "resident" ? h->e.opt_resident : (std::string(name) == "ctas" ? h->e.opt_ctas : h->e.opt_fusepool)) = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
-        return AAU_OK;
+    const std::pair<const char*, int*> plan_options[] = {
+        {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
+        {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"side", &e.opt_side},
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}};
+    for (const auto& o : plan_options) {
+        if (n == o.first) {
+            *o.second = value;
+            e.plans.clear();                                         // launch plans are rebuilt on the next forward
+            e.last_plan = nullptr;
+            return AAU_OK;
+        }
     }
-    if (std::string(name) == "slab_max_bn" || std::string(name) == "mt" || std::string(name) == "cslots") {
-        (std::string(name) == "mt" ? h->e.opt_mt : (std::string(name) == "cslots" ? h->e.opt_cslots : h->e.opt_slab_max_bn)) = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
-        return AAU_OK;
-    }
-    if (std::string(name) == "fixcc") {
-        h->e.opt_fixcc = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
-        return AAU_OK;
-    }
-    if (std::string(name) == "side" || std::string(name) == "pdl" || std::string(name) == "fusefix") {
-        (std::string(name) == "side" ? h->e.opt_side : (std::string(name) == "pdl" ? h->e.opt_pdl : h->e.opt_fusefix)) = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
-        return AAU_OK;
-    }
-    if (std::string(name) == "rs" || std::string(name) == "ng" || std::string(name) == "titer" || std::string(name) == "rs_mt") {
-        (std::string(name) == "rs" ? h->e.opt_rs : (std::string(name) == "ng" ? h->e.opt_ng : (std::string(name) == "titer" ? h->e.opt_titer : h->e.opt_rs_mt))) = value;
-        h->e.plans.clear();
-        h->e.last_plan = nullptr;
-        return AAU_OK;
-    }
-    if (std::string(name) == "profile") {
-        h->e.opt_profile = value;
-        return AAU_OK;
-    }
-    return h->e.fail(AAU_ERR_INVALID, std::string("unknown option ") + name);
+    return e.fail(AAU_ERR_INVALID, std::string("unknown option ") + name);
 }
 
 }  // extern "C"

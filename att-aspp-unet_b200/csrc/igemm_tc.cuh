@@ -35,10 +35,11 @@
 // B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
 //   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 / 6..9 = two epilogue groups (one warp per TMEM lane quarter), group g drains accumulator stage g.  Two accumulator stages in TMEM let the
-// epilogue of tile i overlap the MMAs of tile i+1; small-N layers additionally run 2-3 CTAs per SM, because
-// there the single issuing thread (not the tensor pipe) is the limiter (ncu, profiles/r01_*).
+// Warp roles (64 + 128*NG threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run warp-uniform,
+// the asynchronous instructions under elect.sync), then NG in {2, 4} epilogue groups of four warps (one warp per TMEM
+// lane quarter); group g drains accumulator stage g, so the epilogue of a tile overlaps the MMAs of the next ones.
+// Small-N layers run two CTAs per SM (NG = 2 each) or, when shared memory allows one CTA only, NG = 4: what paces them
+// is the per-tile epilogue latency chain and the shared-memory operand feed, not the tensor pipe (profiles/r01_*).
 //
 // Epilogues (fp32 math on the accumulator, single rounding to the 16-bit activation type):
 //   EPI_STORE   : + bias (per channel or per image), optional ReLU -> swizzled smem -> TMA store into the NHWC
