@@ -668,7 +668,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     int ctas = (BN <= 128) ? 2 : 1;                               // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / cols_for(2));
     if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / cols_for(2));
-    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE;
+    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE && descs.size() == 1;
     // transposed convs with four (a,b) chunks per tile: one CTA with four groups, each staging all four chunks behind a
     // single fence / barrier / store group, beats two CTAs that sync per chunk (A/B on u1.up: -8 %)
     if (d0.epi == EPI_CONVT && ng4_ok && P.MT * BN / P.CB == 4 && e.opt_ctas == 0 && e.opt_cslots == 0 && e.opt_convt_batch != 0) ctas = 1;
@@ -843,8 +843,10 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
-        if (ng == 4) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, false>, Q);
-        return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false>, Q);
+        if (Q.nprob > 1)                                               // several problems per launch: always 2 groups (BN = 256)
+            return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true>, Q);
+        if (ng == 4) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, true, false>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, false, false>, Q);
+        return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, false>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, false>, Q);
     });
     return AAU_OK;
 }
@@ -1164,8 +1166,9 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144) == cudaSuccess &&
                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     };
-    if (!raise_smem((const void*)igemm_tc_kernel<2, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true>) ||
-        !raise_smem((const void*)igemm_tc_kernel<4, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true>)) {
+    if (!raise_smem((const void*)igemm_tc_kernel<2, false, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false>) ||
+        !raise_smem((const void*)igemm_tc_kernel<4, false, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true, false>) ||
+        !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>)) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;

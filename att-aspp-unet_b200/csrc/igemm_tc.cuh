@@ -313,7 +313,7 @@ __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uin
 // must assume divergence, wraps every UTCHMMA in an elect/branch "waterfall" loop and moves each descriptor from
 // vector to uniform registers first (R2UR): ~70-100 cycles per MMA instead of the 40-48 cycle hardware floor of
 // the small-N layers (profiles/r01_mma_probe.txt).
-template <int KK>
+template <int KK, bool MULTI>
 __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a, uint64_t* empty_a,
                                          uint64_t* full_b, uint64_t* empty_b, uint64_t* b_res_bar, uint64_t* tmem_full_bar,
                                          uint64_t* tmem_empty_bar, uint32_t tmem_base) {
@@ -337,7 +337,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     TM_DECL();
     for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
         const TileCoord tc = it.coord(P);
-        const IgemmProblem& q = P.prob[tc.pi];
+        const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
         TM_MARK(2);
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
         ptx::tc_fence_after();
@@ -422,7 +422,9 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 
 // NG = epilogue groups = TMEM accumulator stages (2, or 4 for single-CTA-per-SM layers whose 4 accumulators fit in
 // the 512 TMEM columns: there the per-tile epilogue latency chain, not the tensor pipe, sets the pace).
-template <int NG, bool F16>
+// MULTI = the launch holds several problems (the three dilated ASPP branches); single-problem launches read their
+// problem record at fixed parameter offsets (uniform constant loads the compiler can hoist out of the tile loops).
+template <int NG, bool F16, bool MULTI>
 __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             TileIter it;
             for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
                 const TileCoord tc = it.coord(P);
-                const IgemmProblem& q = P.prob[tc.pi];
+                const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
                 if (P.amode == AMODE_TAP) {
                     const int steps = q.taps * q.nchunk;
                     for (int s = 0; s < steps; ++s) {
@@ -564,9 +566,9 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         {
-            if (P.KC == 64)      mma_role<4>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else if (P.KC == 32) mma_role<2>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else                 mma_role<1>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            if (P.KC == 64)      mma_role<4, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else if (P.KC == 32) mma_role<2, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else                 mma_role<1, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
         }
     } else {
         // =========================== epilogue (warps 2..9) ===========================
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         TM_DECL();
         for (it.init(P, blockIdx.x + grp * gridDim.x, NG * gridDim.x); it.valid(); it.next()) {
             const TileCoord tc = it.coord(P);
-            const IgemmProblem& q = P.prob[tc.pi];
+            const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
             const int xoff = P.amode == AMODE_RS ? 1 : 0;           // RS: output column j sits at slab column j + 1
             const int y = tc.y0 + ty, x = tc.x0 + xoff + tx;
             const bool colok = P.amode != AMODE_RS || tx < P.VW;    // RS: the last two columns of a row are wrap-around garbage
