@@ -620,10 +620,16 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
 #define EPI_BAR()                                                           \
     do {                                                                    \
-        if (grp == 0)      asm volatile("bar.sync 1, 128;" ::: "memory");   \
-        else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");   \
-        else if (grp == 2) asm volatile("bar.sync 3, 128;" ::: "memory");   \
-        else               asm volatile("bar.sync 4, 128;" ::: "memory");   \
+        if (NG == 2) {                          /* two predicated barriers instead of a four-way jump table */ \
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");    \
+            else          asm volatile("bar.sync 2, 128;" ::: "memory");    \
+        } else if (grp < 2) {                                               \
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");    \
+            else          asm volatile("bar.sync 2, 128;" ::: "memory");    \
+        } else {                                                            \
+            if (grp == 2) asm volatile("bar.sync 3, 128;" ::: "memory");    \
+            else          asm volatile("bar.sync 4, 128;" ::: "memory");    \
+        }                                                                   \
     } while (0)
         TileIter it;
         TM_DECL();
