@@ -132,6 +132,7 @@ struct Engine {
     int opt_cslots = 0;
     int opt_rs = 1;
     int opt_titer = 1;
+    int opt_lean = 1;
     int opt_rs_mt = 0;                                // 0: planner's rule, 1: never, 2: always two M-blocks per row-shifted tile
     int opt_ng = 0;                                   // 0: planner's choice, 2 / 4: force the number of epilogue groups
     int opt_ctas = 0;
@@ -720,6 +721,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.b_region_bytes = b_region;
     P.is_fp16 = e.is_fp16() ? 1 : 0;
     P.tile_iter = e.opt_titer;
+    P.lean_sync = e.opt_lean;
     P.err = e.d_err;
     P.nprob = (int)descs.size();
     int tile_begin = 0;
@@ -1479,7 +1481,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
         {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"side", &e.opt_side},
-        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}};
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {
             *o.second = value;

@@ -144,6 +144,7 @@ struct alignas(64) IgemmParams {
     int tmem_cols;
     int acc_stages;         // TMEM accumulator stages (2, or 1 when 2*BN columns would leave no room for a second CTA)
     int is_fp16;
+    int lean_sync;          // 1: drop the per-tile top barrier where a static bias and alternating staging tiles allow it
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int* err;
 };
@@ -616,6 +617,14 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                           : q0.epi == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
         }
         const uint32_t smem_c_u32 = ptx::smem_u32(smem_c), smem_p_u32 = ptx::smem_u32(smem_p);
+        // The barrier at the top of a tile publishes the tile's bias and the "staging tile is free again" news.  With a
+        // static bias it can go when nothing is staged (OUTCONV), or when tiles are single-chunk STOREs alternating
+        // between two staging tiles: there thread 0 waits for the PREVIOUS tile's store to have read its tile right
+        // before the mid-tile barrier every thread passes anyway (that store was issued a whole tile ago).
+        const int epi0 = P.prob[0].epi;
+        const int chunks_per_tile = P.amode == AMODE_DXN ? 1 : P.MT * P.BN / P.CB;
+        const bool early_wait = bias_static && !P.cbatch && P.cslots == 2 && chunks_per_tile == 1 && epi0 == EPI_STORE && P.lean_sync != 0;
+        const bool skip_top_bar = bias_static && P.lean_sync != 0 && (epi0 == EPI_OUTCONV || early_wait);
         asm volatile("griddepcontrol.wait;" ::: "memory");          // before the first store / activation read of this role
         // immediate barrier ids: a register operand would make ptxas reserve all 16 hardware barriers per CTA
 #define EPI_BAR()                                                           \
@@ -631,6 +640,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             else          asm volatile("bar.sync 4, 128;" ::: "memory");    \
         }                                                                   \
     } while (0)
+        if (skip_top_bar) EPI_BAR();                                 // the static bias becomes visible once
         TileIter it;
         TM_DECL();
         for (it.init(P, blockIdx.x + grp * gridDim.x, NG * gridDim.x); it.valid(); it.next()) {
@@ -651,13 +661,13 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                           : q.epi == EPI_CONVTFIX ? ((tc.n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q.convt_cout : tc.n0 + i));
             }
             TM_MARK(0);                                         // 0: tile bookkeeping
-            if (etid == 0) WAIT_STORE_READS();                  // the store that last used the next staging tile has left smem
+            if (etid == 0 && !skip_top_bar) WAIT_STORE_READS(); // the store that last used the next staging tile has left smem
             TM_MARK(1);                                         // 1: wait for the previous TMA store to have read its tile
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
             acc_phase ^= 1;
             ptx::tc_fence_after();
             TM_MARK(2);                                         // 2: wait for the accumulator
-            EPI_BAR();                                          // bias visible, staging tiles free
+            if (!skip_top_bar) EPI_BAR();                       // bias visible, staging tiles free
             TM_MARK(3);                                         // 3: group barrier at the top
             const uint32_t taddr0 = tmem_base + (uint32_t)(acc * P.BN * P.MT) + ((uint32_t)(quarter * 32) << 16);
             uint32_t taddr = taddr0;
@@ -713,6 +723,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                 if (q.epi == EPI_STORE) {
+                    if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
                     if (P.pool) {
@@ -797,6 +808,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     }
                     TM_MARK(4);                                                 // 4: TMEM -> registers -> staged tile
                     if (!batch) {
+                        if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                         TM_MARK(5);                                             // 5: proxy fence + barrier
