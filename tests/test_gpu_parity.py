@@ -283,3 +283,20 @@ def test_fused_transposed_conv_and_bilinear_fixup(c, shape):
     assert e_f.max().item() <= 0.03 * spread + 2e-2
     assert e_f.mean().item() <= 1.1 * e_s.mean().item() + 1e-5       # single rounding: never worse than convT -> store -> resize
     assert agreement(fused, ref, 0.5) >= 0.995
+
+
+# ------------------------------------------------------------------------------------------------ small / odd shapes
+@pytest.mark.parametrize("c,shape", [(16, (1, 16, 16)), (16, (2, 17, 33)), (16, (1, 31, 64)), (16, (3, 48, 50)), (16, (1, 95, 161)),
+                                     (16, (2, 64, 36)), (32, (1, 33, 47)), (32, (5, 18, 130))])
+def test_small_and_odd_shapes(c, shape):
+    """Planner corner cases: frames smaller than a tile, widths below one row-shifted tile, odd sizes at every level."""
+    cfg = O.NetCfg(base_c=c)
+    sd, x = r1_case(cfg, shape, seed=3)
+    ref = O.forward(sd, x, cfg)
+    net = make_net(cfg, sd, "fp16")
+    out = net(x.cuda()).cpu()
+    net.check_device()
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    spread = ref.std().item()
+    assert (out - ref).abs().max().item() <= 0.03 * spread + 2e-2
+    assert agreement(out, ref, 0.5) >= 0.99
