@@ -123,6 +123,7 @@ struct Engine {
     int opt_fusefix = 1;
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
+    int opt_pair = 1;
     int last_launches = 0;
     int opt_amode = -1;
     int opt_resident = 1;
@@ -647,7 +648,11 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     const int swz = P.KC * 2;
     const int nchunk = Cin / P.KC;
     const int steps = (dxn ? 3 : d0.w->taps) * nchunk;            // k-steps (one B sub-block each) per tile
-    P.b_slot_bytes = BN * swz;
+    // CTA pairs (cta_group::2): slab-staged layers whose weights stream, one N tile, an even number of tiles
+    const int tiles_total0 = d0.in.B * ((W + P.VW - 1) / P.VW) * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
+    const bool pair = e.opt_pair != 0 && slab && !dxn && !rs && descs.size() == 1 && d0.epi == EPI_STORE && Ntot == BN && BN >= 128 &&
+                      (size_t)9 * Cin * BN * 2 > 112 * 1024 && tiles_total0 % 2 == 0 && tiles_total0 >= 2;
+    P.b_slot_bytes = (pair ? BN / 2 : BN) * swz;
     P.a_slot_bytes = slab ? (((P.TH * P.MT + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
     // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
     const bool tma_out = d0.epi == EPI_STORE || d0.epi == EPI_CONVT || d0.epi == EPI_GATE || cfix;
@@ -663,13 +668,13 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // CTA fits and four accumulators fit in the 512 TMEM columns, that CTA runs 4 stages / groups instead.
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
     // n_tiles so that the static striding keeps every CTA on the same N tile
-    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0;
+    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0 && !pair;
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
     auto cols_for = [&](int stages) { int c = 32; while (c < stages * BN * P.MT) c <<= 1; return c; };
-    int ctas = (BN <= 128) ? 2 : 1;                               // measured: 2 CTAs co-reside, a third only queues
+    int ctas = (BN <= 128 && !pair) ? 2 : 1;                      // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / cols_for(2));
     if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / cols_for(2));
-    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE && descs.size() == 1;
+    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE && descs.size() == 1 && !pair;
     // transposed convs with four (a,b) chunks per tile: one CTA with four groups, each staging all four chunks behind a
     // single fence / barrier / store group, beats two CTAs that sync per chunk (A/B on u1.up: -8 %)
     if (d0.epi == EPI_CONVT && ng4_ok && P.MT * BN / P.CB == 4 && e.opt_ctas == 0 && e.opt_cslots == 0 && e.opt_convt_batch != 0) ctas = 1;
@@ -739,7 +744,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
         const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
         const uint64_t bstr[1] = {bdims[0] * 2};
-        const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)BN};
+        const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)(pair ? BN / 2 : BN)};
         if (!encode_map(e, &q.tmB, dxn ? d.w->dBdx : d.w->dB, 2, bdims, bstr, bbox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight tensor");
         q.bias = d.bias_img ? d.bias_img : d.w->dbias;
@@ -823,14 +828,15 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // not, the second half of the grid would simply run as a second wave over the same static tile striding.
     int grid = std::min(P.total_tiles, e.num_sms * ctas);
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
+    if (pair) grid &= ~1;                                          // clusters of two
     oi.name += " [" + std::string(cfix ? "tap2+fix" : (rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap")))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
-               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + (pair ? " pair" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
     const bool f16k = e.is_fp16();
     // programmatic dependent launch when the op before this one in the stream is a kernel (not the side-stream join)
     const bool pdl = e.opt_pdl != 0 && plan.info.size() >= 2 && plan.info[plan.info.size() - 2].kernel[0] != '(';
-    plan.ops.push_back([P, grid, smem, patch_aux, ng, f16k, pdl](const FwdArgs& a) -> cudaError_t {
+    plan.ops.push_back([P, grid, smem, patch_aux, ng, f16k, pdl, pair](const FwdArgs& a) -> cudaError_t {
         IgemmParams Q = P;
         if (patch_aux == 1) Q.prob[0].aux = a.logits;
         if (patch_aux == 2) Q.prob[0].aux = a.psi3;
@@ -840,11 +846,23 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         cfg.blockDim = dim3((unsigned)igemm_threads(ng));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = a.stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (pair) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = pdl ? 1 : 0;
+        cfg.numAttrs = na;
+        if (pair) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, false, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, false, true>, Q);
         if (Q.nprob > 1)                                               // several problems per launch: always 2 groups (BN = 256)
             return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true>, Q);
         if (ng == 4) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, true, false>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, false, false>, Q);
@@ -1170,7 +1188,8 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
     };
     if (!raise_smem((const void*)igemm_tc_kernel<2, false, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false>) ||
         !raise_smem((const void*)igemm_tc_kernel<4, false, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true, false>) ||
-        !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>)) {
+        !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>) ||
+        !raise_smem((const void*)igemm_tc_kernel<2, false, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false, true>)) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;
@@ -1480,7 +1499,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

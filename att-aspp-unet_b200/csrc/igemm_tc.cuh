@@ -296,14 +296,15 @@ __device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int t
 
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
 // field, so stepping K by 32 bytes is "+2" on the low word.
-template <int KK>
+template <int KK, bool PAIR = false>
 __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                              uint32_t accumulate) {
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
         const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
         const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
-        ptx::umma_f16(d_tmem, da, db, idesc, accumulate);
+        if (PAIR) ptx::umma_f16_pair(d_tmem, da, db, idesc, accumulate);
+        else      ptx::umma_f16(d_tmem, da, db, idesc, accumulate);
         accumulate = 1;
     }
 }
@@ -314,12 +315,12 @@ __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uin
 // must assume divergence, wraps every UTCHMMA in an elect/branch "waterfall" loop and moves each descriptor from
 // vector to uniform registers first (R2UR): ~70-100 cycles per MMA instead of the 40-48 cycle hardware floor of
 // the small-N layers (profiles/r01_mma_probe.txt).
-template <int KK, bool MULTI>
+template <int KK, bool MULTI, bool PAIR>
 __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a, uint64_t* empty_a,
                                          uint64_t* full_b, uint64_t* empty_b, uint64_t* b_res_bar, uint64_t* tmem_full_bar,
                                          uint64_t* tmem_empty_bar, uint32_t tmem_base) {
     const int swz = P.KC * 2;
-    const uint32_t idesc = ptx::make_idesc_f16(128, P.BN, P.is_fp16 != 0);
+    const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 256 : 128, P.BN, P.is_fp16 != 0);   // pair: M = 256 over the two CTAs
     const uint64_t proto = ptx::make_kmajor_desc(0, swz);
     const uint32_t desc_hi = (uint32_t)(proto >> 32);
     const uint32_t lo_flags = (uint32_t)proto;                               // LBO field; start address = 0
@@ -400,11 +401,11 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                     if (ptx::elect_one()) {
                         if (P.MT == 2) {                                      // second M-block: TH rows further down the slab
                             uint32_t acc2 = accumulate;
-                            mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
+                            mma_subblock<KK, PAIR>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
                         }
-                        mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                        if (!res) ptx::umma_commit(&empty_b[ib]);
-                        if (dyi == 2) ptx::umma_commit(&empty_a[ia]);
+                        mma_subblock<KK, PAIR>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                        if (!res) { if (PAIR) ptx::umma_commit_pair(&empty_b[ib]); else ptx::umma_commit(&empty_b[ib]); }
+                        if (dyi == 2) { if (PAIR) ptx::umma_commit_pair(&empty_a[ia]); else ptx::umma_commit(&empty_a[ia]); }
                     }
                     __syncwarp();
                     accumulate = 1;
@@ -413,7 +414,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 if (++ia == P.nA) { ia = 0; pa ^= 1; }
             }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+        if (ptx::elect_one()) {                                               // accumulator complete -> epilogue (of both CTAs of a pair)
+            if (PAIR) ptx::umma_commit_pair(&tmem_full_bar[acc]);
+            else      ptx::umma_commit(&tmem_full_bar[acc]);
+        }
         __syncwarp();
         if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
@@ -425,7 +429,11 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 // the 512 TMEM columns: there the per-tile epilogue latency chain, not the tensor pipe, sets the pace).
 // MULTI = the launch holds several problems (the three dilated ASPP branches); single-problem launches read their
 // problem record at fixed parameter offsets (uniform constant loads the compiler can hoist out of the tile loops).
-template <int NG, bool F16, bool MULTI>
+// PAIR = launched as clusters of two CTAs that share every MMA (cta_group::2, M = 256): each CTA stages its own A slabs
+// and HALF of each weight sub-block, so the L2 -> SM weight traffic and the shared-memory operand reads per SM drop.
+// Used for the slab-staged layers whose weights stream (N = 128 / 256); the leader (cluster rank 0) issues the MMAs,
+// both CTAs run their own producer and epilogue groups on their own 128 rows.
+template <int NG, bool F16, bool MULTI, bool PAIR = false>
 __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
@@ -457,18 +465,20 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         for (int a = 0; a < NG; ++a) {
             ptx::mbar_init(&c_load_bar[a], 1);
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 4);     // one arrive per epilogue warp of the owning group
+            ptx::mbar_init(&tmem_empty_bar[a], PAIR ? 8 : 4);   // one arrive per epilogue warp of the owning group (of both CTAs)
         }
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&tmem_base_smem, (uint32_t)P.tmem_cols);
-        ptx::tmem_relinquish();
+        if (PAIR) { ptx::tmem_alloc_pair(&tmem_base_smem, (uint32_t)P.tmem_cols); ptx::tmem_relinquish_pair(); }
+        else      { ptx::tmem_alloc(&tmem_base_smem, (uint32_t)P.tmem_cols); ptx::tmem_relinquish(); }
     }
+    const uint32_t pair_rank = PAIR ? ptx::cluster_ctarank() : 0u;
     if (threadIdx.x >= 64 && P.prob[0].vec != nullptr)                        // GATE / OUTCONV vector, constant per launch
         for (int i = threadIdx.x - 64; i < P.n_out; i += 128 * NG) s_vec[i] = P.prob[0].vec[i];
     ptx::tc_fence_before();
     __syncthreads();
+    if (PAIR) ptx::cluster_sync_all();                      // the peer's barriers exist before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     // Programmatic dependent launch: let the next kernel of the stream be scheduled onto SMs as our CTAs retire (its
@@ -540,9 +550,15 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         for (int ch = 0; ch < q.nchunk; ++ch) {
                             ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                             if (ptx::elect_one()) {
-                                ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
-                                ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
-                                                 one_slab ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                                if (PAIR) {                                   // both CTAs' slabs complete the LEADER's barrier
+                                    if (pair_rank == 0) ptx::mbar_expect_tx(&full_a[ia], 2 * slab_bytes);
+                                    ptx::tma_load_4d_pair(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
+                                                          tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                                } else {
+                                    ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
+                                    ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
+                                                     one_slab ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                                }
                             }
                             __syncwarp();
                             if (++ia == P.nA) { ia = 0; pa ^= 1; }
@@ -550,10 +566,16 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                                     if (ptx::elect_one()) {
-                                        ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
-                                        ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
-                                                         dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC,
-                                                         dxn ? (tc.n0 / P.n_out) * P.BN : tc.n0);
+                                        if (PAIR) {                           // this CTA's half of the weight rows
+                                            if (pair_rank == 0) ptx::mbar_expect_tx(&full_b[ib], 2 * (uint32_t)P.b_slot_bytes);
+                                            ptx::tma_load_2d_pair(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
+                                                                  (dyi * 3 + dxi) * cin + ch * P.KC, tc.n0 + (int)pair_rank * (P.BN / 2));
+                                        } else {
+                                            ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                                            ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib],
+                                                             dxn ? dyi * cin + ch * P.KC : (dyi * 3 + dxi) * cin + ch * P.KC,
+                                                             dxn ? (tc.n0 / P.n_out) * P.BN : tc.n0);
+                                        }
                                     }
                                     __syncwarp();
                                     if (++ib == P.nB) { ib = 0; pb ^= 1; }
@@ -566,10 +588,10 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        {
-            if (P.KC == 64)      mma_role<4, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else if (P.KC == 32) mma_role<2, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else                 mma_role<1, MULTI>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+        if (!PAIR || pair_rank == 0) {                      // pair: only the leader issues MMAs
+            if (P.KC == 64)      mma_role<4, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else if (P.KC == 32) mma_role<2, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else                 mma_role<1, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
         }
     } else {
         // =========================== epilogue (warps 2..9) ===========================
@@ -721,7 +743,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
                 if (q.epi == EPI_STORE) {
                     if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -804,7 +826,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (c0 + P.CB >= P.BN && mb == P.MT - 1) {                // accumulator fully read: free the TMEM stage
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
                     }
                     TM_MARK(4);                                                 // 4: TMEM -> registers -> staged tile
                     if (!batch) {
@@ -892,7 +914,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (c0 + P.CB >= CC) {                                      // accumulator fully read: free the TMEM stage
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
@@ -925,7 +947,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
                 if (q.epi == EPI_OUTCONV) {
                     if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 } else {
@@ -974,9 +996,11 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (PAIR) ptx::cluster_sync_all();                      // both CTAs are done with each other's barriers and TMEM
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)P.tmem_cols);
+        else      ptx::tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
     }
 }
 

@@ -135,6 +135,83 @@ __global__ void __launch_bounds__(256) tmem_ld_kernel(int cols, int reps, ProbeO
     if (threadIdx.x < 32) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base_s, 256); }
 }
 
+// ---- 4. CTA pair: tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = 64 with the B rows split across the pair
+//  A_r[m][k] (CTA r, 128 x 64), B[n][k] (64 x 64; CTA r holds rows n in [32r, 32r+32)), D = A . B^T
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_mma_kernel(float* dout /* [256][64] */, int* status) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t rank = cluster_ctarank();
+    uint8_t* sa = smem;                   // 128 rows x 128 B (K = 64 bf16), 128B swizzle
+    uint8_t* sb = smem + 16384;           // 32 rows x 128 B: this CTA's half of B
+    for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+        const int m = i / 64, k = i % 64;
+        const float v = (float)(((m + 128 * (int)rank) % 7) - 3) + (k == (m % 64) ? 0.5f : 0.f);   // small integers / halves: exact in bf16
+        uint32_t off = (uint32_t)(m * 128 + k * 2);
+        off ^= ((off >> 7) & 7) << 4;
+        *reinterpret_cast<__nv_bfloat16*>(sa + off) = __float2bfloat16(v);
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+        const int nl = i / 64, k = i % 64, n = nl + 32 * (int)rank;
+        const float v = (float)(((n * 3 + k) % 5) - 2);
+        uint32_t off = (uint32_t)(nl * 128 + k * 2);
+        off ^= ((off >> 7) & 7) << 4;
+        *reinterpret_cast<__nv_bfloat16*>(sb + off) = __float2bfloat16(v);
+    }
+    if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(&tmem_base_s)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // both CTAs have their operands and barriers ready
+    ptx::tc_fence_after();
+    const uint32_t tm = tmem_base_s;
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (rank == 0 && warp_u == 0) {
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_f16(256, 64, false);
+            const uint64_t da = ptx::make_kmajor_desc(ptx::smem_u32(sa), 128), db = ptx::make_kmajor_desc(ptx::smem_u32(sb), 128);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = k > 0;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                             ::"r"(tm), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(ptx::smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        }
+        __syncwarp();
+    }
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait(&bar, 0)) {
+        if (++spins > (1u << 20)) { if (threadIdx.x == 0) atomicExch(status, 100 + (int)rank); break; }
+    }
+    ptx::tc_fence_after();
+    const int warp = threadIdx.x >> 5;
+    uint32_t r[32];
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        ptx::tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16) + c0, r);
+        ptx::tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) dout[(size_t)(128 * rank + threadIdx.x) * 64 + c0 + i] = __uint_as_float(r[i]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x < 32) {
+        ptx::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(64u) : "memory");
+    }
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main() {
@@ -193,6 +270,42 @@ int main() {
                 }
             printf("row0 %d base_offset_field %d : %d wrong of 8192 (D[0][0..2] = %g %g %g, D[1][0..2] = %g %g %g)\n", row0, ubo, bad, ho[0], ho[1], ho[2], ho[64], ho[65], ho[66]);
         }
+    }
+    printf("# 4. CTA pair MMA (cta_group::2, M=256, N=64, B rows split across the pair)\n");
+    {
+        CK(cudaFuncSetAttribute(pair_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        float* dd; int* st;
+        CK(cudaMalloc(&dd, 256 * 64 * 4)); CK(cudaMalloc(&st, 4)); CK(cudaMemset(st, 0, 4)); CK(cudaMemset(dd, 0xff, 256 * 64 * 4));
+        pair_mma_kernel<<<2, 128, 40 * 1024>>>(dd, st);
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("launch: %s\n", cudaGetErrorString(e));
+        if (e == cudaSuccess) {
+            std::vector<float> hd(256 * 64); int hs = 0;
+            CK(cudaMemcpy(hd.data(), dd, hd.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&hs, st, 4, cudaMemcpyDeviceToHost));
+            int bad = 0, bad_hi = 0;
+            for (int m = 0; m < 256; ++m)
+                for (int n = 0; n < 64; ++n) {
+                    float want = 0.f;
+                    for (int k = 0; k < 64; ++k) {
+                        const float a = (float)(((m) % 7) - 3) + (k == ((m % 128) % 64) ? 0.5f : 0.f);
+                        const float b = (float)(((n * 3 + k) % 5) - 2);
+                        want += a * b;
+                    }
+                    if (hd[m * 64 + n] != want) { ++bad; if (m >= 128) ++bad_hi; }
+                }
+            int colbad[8] = {0}, rowbad[8] = {0};
+            for (int m = 0; m < 256; ++m)
+                for (int n = 0; n < 64; ++n) {
+                    float want = 0.f;
+                    for (int k = 0; k < 64; ++k) want += ((float)((m % 7) - 3) + (k == ((m % 128) % 64) ? 0.5f : 0.f)) * (float)(((n * 3 + k) % 5) - 2);
+                    if (hd[m * 64 + n] != want) { ++colbad[n / 8]; ++rowbad[m / 32]; }
+                }
+            printf("wrong per 8-column group:"); for (int i = 0; i < 8; ++i) printf(" %d", colbad[i]);
+            printf("\nwrong per 32-row group:"); for (int i = 0; i < 8; ++i) printf(" %d", rowbad[i]);
+            printf("\nrow 5: "); for (int n = 0; n < 64; ++n) printf("%g ", hd[5 * 64 + n]); printf("\n");
+            printf("status %d, wrong %d of 16384 (%d in the second CTA's rows); D[0][0..3] = %g %g %g %g, D[128][0..3] = %g %g %g %g\n", hs, bad, bad_hi,
+                   hd[0], hd[1], hd[2], hd[3], hd[128 * 64], hd[128 * 64 + 1], hd[128 * 64 + 2], hd[128 * 64 + 3]);
+        } else return 0;
     }
     printf("# 3. tcgen05.ld 32x32b.x32 throughput, one CTA per SM\n");
     for (int threads : {128, 256}) {
