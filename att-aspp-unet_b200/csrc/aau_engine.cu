@@ -43,6 +43,7 @@ struct KeySpec {
 struct GemmW {                // packed GEMM operand, device resident
     void* dB = nullptr;       // [N][K] 16-bit, K contiguous
     void* dBdx = nullptr;     // 3x3 only, N in {16,32,64}: [3N][3Cin], row (h*3+j)*dx_nt+o' = W[h*dx_nt+o'][:][dy][dx=j] (AMODE_DXN)
+    void* dBdx_full = nullptr; // the same with all N output channels in one tile, when those weights (112..144 KB) can stay resident
     int dx_nt = 0;            // output channels per dx-stacked tile (N, or N/2 so that one tile's weights fit in smem)
     float* dbias = nullptr;   // fp32
     float* dvec = nullptr;    // optional fp32 vector (gate w_psi, out_conv w)
@@ -124,6 +125,7 @@ struct Engine {
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
     int opt_pair = 1;
+    int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
     int last_launches = 0;
     int opt_amode = -1;
     int opt_resident = 1;
@@ -307,17 +309,24 @@ static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::
         int nt = cout;
         while (nt > 16 && (size_t)3 * nt * 3 * cin * 2 > 112 * 1024) nt >>= 1;
         g.dx_nt = nt;
-        std::vector<uint16_t> bd((size_t)3 * cout * 3 * cin);
         const bool f16 = e.is_fp16();
-        for (int j = 0; j < 3; ++j)
-            for (int o = 0; o < cout; ++o)
-                for (int dy = 0; dy < 3; ++dy)
-                    for (int i = 0; i < cin; ++i)
-                        bd[((size_t)((o / nt) * 3 + j) * nt + (o % nt)) * 3 * cin + (size_t)dy * cin + i] =
-                            to16((float)((double)(*w)[((size_t)o * cin + i) * 9 + dy * 3 + j] * s[o]), f16);
-        uint16_t* d = nullptr;
-        if (upload(e, bd, &d) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "weight upload failed");
-        g.dBdx = d;
+        auto stack = [&](int tile_n, void** out) -> bool {
+            std::vector<uint16_t> bd((size_t)3 * cout * 3 * cin);
+            for (int j = 0; j < 3; ++j)
+                for (int o = 0; o < cout; ++o)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int i = 0; i < cin; ++i)
+                            bd[((size_t)((o / tile_n) * 3 + j) * tile_n + (o % tile_n)) * 3 * cin + (size_t)dy * cin + i] =
+                                to16((float)((double)(*w)[((size_t)o * cin + i) * 9 + dy * 3 + j] * s[o]), f16);
+            uint16_t* d = nullptr;
+            if (upload(e, bd, &d) != cudaSuccess) return false;
+            *out = d;
+            return true;
+        };
+        if (!stack(nt, &g.dBdx)) return e.fail(AAU_ERR_CUDA, "weight upload failed");
+        // un-split variant for weights of 112..144 KB: they still fit beside 32-channel A slabs (see add_igemm)
+        if (nt != cout && (size_t)3 * cout * 3 * cin * 2 <= 144 * 1024 && cin % 32 == 0)
+            if (!stack(cout, &g.dBdx_full)) return e.fail(AAU_ERR_CUDA, "weight upload failed");
     }
     e.gw[name] = g;
     return r;
@@ -601,12 +610,25 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
                (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && (e.opt_amode < 0 || e.opt_amode == 2);
     if (dxn && d0.epi == EPI_OUTCONV && d0.w->dx_nt != Ntot) dxn = false;
     int n_out = BN;
+    // un-split dx-stacked weights of 112..144 KB (u2.conv.0, 128 -> 64): resident next to three 32-channel A slabs.  One
+    // N' = 192 MMA per 16 channels instead of two N' = 96 ones over the same slab: the slab is loaded once, not twice, and
+    // the single issuing warp -- the pacing resource of the split form (tools/phase_timing.py) -- has 96 cycles per MMA.
+    bool dxn_full = dxn && d0.w->dBdx_full != nullptr && e.opt_dxn_full != 0 && e.opt_resident != 0 && d0.epi == EPI_STORE;
+    size_t res_limit = 112 * 1024;
     if (dxn) {                                                     // does the dx-stacked pipeline fit in shared memory?
-        n_out = d0.w->dx_nt;
-        const int sw = P.KC * 2, a = 6 * 32 * sw, b = 3 * n_out * sw, st = 3 * (Cin / P.KC);
-        const int rb = (st * b + 1023) & ~1023, cb = (d0.epi == EPI_STORE ? 2 * 128 * n_out * 2 : 0) + (want_pool ? 8192 : 0), budget1 = 225280;
-        const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * a + 4 * b <= budget1);
-        if (!fits) { dxn = false; n_out = BN; }
+        const int budget1 = 225280;
+        if (dxn_full) {
+            const int sw = 64, a = 6 * 32 * sw, rb = 3 * Ntot * 3 * Cin * 2, cb = 2 * 128 * Ntot * 2 + (want_pool ? 8192 : 0);
+            if (cb + rb + 3 * a <= budget1) { P.KC = 32; n_out = Ntot; res_limit = 144 * 1024; }
+            else dxn_full = false;
+        }
+        if (!dxn_full) {
+            n_out = d0.w->dx_nt;
+            const int sw = P.KC * 2, a = 6 * 32 * sw, b = 3 * n_out * sw, st = 3 * (Cin / P.KC);
+            const int rb = (st * b + 1023) & ~1023, cb = (d0.epi == EPI_STORE ? 2 * 128 * n_out * 2 : 0) + (want_pool ? 8192 : 0);
+            const bool fits = (e.opt_resident != 0 && rb <= 112 * 1024 && cb + rb + 2 * a <= budget1) || (cb + 2 * a + 4 * b <= budget1);
+            if (!fits) { dxn = false; n_out = BN; }
+        }
     }
     // row-shifted taps (AMODE_RS): small-N 3x3 layers whose whole weight matrix stays in shared memory and whose K is
     // small enough that nine N-wide MMAs per 16 channels (32 + N/4 cycles each) stay under the HBM time of the tile
@@ -690,7 +712,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             // passes 3-5: the same with streamed weights
             const int nchunks = (P.amode == AMODE_DXN) ? 1 : P.MT * BN / P.CB;
             for (int pass = 0; pass < 6 && !ok; ++pass) {
-                const bool res = pass < 3 && can_res && steps <= 64 && res_bytes <= 112 * 1024;
+                const bool res = pass < 3 && can_res && steps <= 64 && (size_t)res_bytes <= res_limit;
                 if (pass < 3 && !res) continue;
                 if (rs && !res) continue;                          // row-shifted taps index the resident weight matrix
                 const int sel = pass % 3;
@@ -745,7 +767,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
         const uint64_t bstr[1] = {bdims[0] * 2};
         const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)(pair ? BN / 2 : BN)};
-        if (!encode_map(e, &q.tmB, dxn ? d.w->dBdx : d.w->dB, 2, bdims, bstr, bbox, swz))
+        if (!encode_map(e, &q.tmB, dxn ? (dxn_full ? d.w->dBdx_full : d.w->dBdx) : d.w->dB, 2, bdims, bstr, bbox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight tensor");
         q.bias = d.bias_img ? d.bias_img : d.w->dbias;
         q.bias_img_stride = d.bias_img ? d.bias_img_stride : 0;
@@ -1499,7 +1521,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

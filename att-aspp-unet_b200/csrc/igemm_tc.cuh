@@ -391,8 +391,32 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             int step = 0;
             const int ndc = (P.amode == AMODE_SLAB ? 3 : 1) * q.nchunk;
             for (int dc = 0; dc < ndc; ++dc) {                                // SLAB: (dx, channel chunk); DXN: channel chunk
+                TM_MARK(2);
                 ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                TM_MARK(1);
                 const uint32_t a_lo = a_base + ia * a_slot16;
+                if (res && !PAIR) {
+                    // resident weights: nothing to wait for between the vertical taps, so all of them go out under one
+                    // election (a fence + elect + warp sync per four MMAs kept the issue rate of the one-CTA-per-SM
+                    // dx-stacked layer at 87 cycles per MMA against the 56-cycle operand-read floor)
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            const uint32_t b_lo = b_base + (uint32_t)(step + dyi) * b_slot16;
+                            if (P.MT == 2)
+                                mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
+                            mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
+                        }
+                        ptx::umma_commit(&empty_a[ia]);
+                    }
+                    __syncwarp();
+                    step += 3;
+                    accumulate = 1;
+                    TM_MARK(3);
+                    if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                    continue;
+                }
 #pragma unroll
                 for (int dyi = 0; dyi < 3; ++dyi, ++step) {
                     const int bslot = res ? step : ib;
@@ -411,6 +435,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                     accumulate = 1;
                     if (!res && ++ib == P.nB) { ib = 0; pb ^= 1; }
                 }
+                TM_MARK(3);
                 if (++ia == P.nA) { ia = 0; pa ^= 1; }
             }
         }

@@ -242,7 +242,8 @@ OPTION_SETS = [
     {"ng": 2, "ctas": 1, "cslots": 1},
     {"resident": 0},                # weights streamed through the B ring
     {"titer": 0, "pdl": 0, "side": 0, "fusepool": 0},
-    {"pair": 0, "lean": 0, "convt_batch": 0},   # no CTA pairs (cta_group::2), per-tile top barrier everywhere, per-chunk transposed-conv sync
+    {"pair": 0, "lean": 0, "convt_batch": 0},
+    {"dxn_full": 0},                            # u2.conv.0 with its dx-stacked weights split in two N tiles   # no CTA pairs (cta_group::2), per-tile top barrier everywhere, per-chunk transposed-conv sync
 ]
 
 
