@@ -125,6 +125,7 @@ struct Engine {
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
     int opt_pair = 1;
+    int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
     int last_launches = 0;
     int opt_amode = -1;
@@ -647,25 +648,27 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // tile shape: minimise padded pixels (and, for slabs, halo overhead)
     // (the fused transposed-conv + fix-up GEMM has one extra row / column: output 2n holds transposed-conv row 2n-1)
     const int H = d0.in.H + (cfix && d0.fix_axis == 0 ? 1 : 0), W = d0.in.W + (cfix && d0.fix_axis == 1 ? 1 : 0);
+    // two vertically stacked M-blocks per tile when the weights stream through the B ring (halves their L2->SM traffic)
+    // ... and for row-shifted taps whose resident weights leave room for one CTA per SM only: a 256-pixel tile halves the
+    // per-tile bookkeeping / barrier cost of the epilogue groups (the pacing resource of those layers, tools/phase_timing.py)
+    // and lowers the halo overhead from 6/4 to 10/8.  Measured A/B (B200, batch 28): u2.conv.1 -12 %, d2.1 (fused pool) +1 %,
+    // d1.1 / d2.0 (two CTAs per SM) +11..19 % -> only the first kind gets it.  CTA pairs keep it (u3.conv +19 % without).
+    const bool mt_stream = slab && !dxn && !rs && BN <= 128 && (size_t)9 * Cin * BN * 2 > 112 * 1024;
+    const bool mt_rs = rs && (e.opt_rs_mt == 2 || (e.opt_rs_mt == 0 && (size_t)9 * Cin * BN * 2 > 64 * 1024 && !want_pool));
+    const int mt_want = ((mt_stream || mt_rs) && d0.epi == EPI_STORE && e.opt_mt == 2) ? 2 : 1;
     double best = 1e30;
     for (int tw = 8; tw <= 128; tw <<= 1) {
         const int th = 128 / tw;
         if (slab && th < 4) continue;
         if (want_pool && th < 2) continue;
-        double cost = (double)((H + th - 1) / th * th) * ((W + tw - 1) / tw * tw);
-        if (slab) cost *= 1.0 + 0.5 * 2.0 / th;     // halo rows cost bandwidth, not MMA time
+        const int mt = (mt_want == 2 && H > th && e.opt_mt_shape != 0) ? 2 : 1;   // rows of a tile: th * mt
+        double cost = (double)((H + th * mt - 1) / (th * mt) * (th * mt)) * ((W + tw - 1) / tw * tw);
+        if (slab) cost *= 1.0 + 0.5 * 2.0 / (th * mt);     // halo rows cost bandwidth, not MMA time
         if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
     }
     P.VW = P.TW;
     if (dxn || rs) { P.TW = 32; P.TH = 4; P.VW = 30; }
-    // two vertically stacked M-blocks per tile when the weights stream through the B ring (halves their L2->SM traffic)
-    // ... and for row-shifted taps whose resident weights leave room for one CTA per SM only: a 256-pixel tile halves the
-    // per-tile bookkeeping / barrier cost of the epilogue groups (the pacing resource of those layers, tools/phase_timing.py)
-    // and lowers the halo overhead from 6/4 to 10/8.  Measured A/B (B200, batch 28): u2.conv.1 -12 %, d2.1 (fused pool) +1 %,
-    // d1.1 / d2.0 (two CTAs per SM) +11..19 % -> only the first kind gets it.
-    const bool mt_stream = slab && !dxn && !rs && BN <= 128 && (size_t)9 * Cin * BN * 2 > 112 * 1024;
-    const bool mt_rs = rs && (e.opt_rs_mt == 2 || (e.opt_rs_mt == 0 && (size_t)9 * Cin * BN * 2 > 64 * 1024 && !want_pool));
-    P.MT = ((mt_stream || mt_rs) && d0.epi == EPI_STORE && e.opt_mt == 2 && H > P.TH) ? 2 : 1;
+    P.MT = (mt_want == 2 && H > P.TH) ? 2 : 1;
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
     const int nchunk = Cin / P.KC;
@@ -1521,7 +1524,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

@@ -624,12 +624,16 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         // accumulator stage g, i.e. every second tile of this CTA.  Per tile the epilogue is a latency chain
         // (tmem wait -> tcgen05.ld -> math -> smem -> proxy fence -> barrier -> TMA store), not a throughput problem
         // (ncu: profiles/r01_ncu_dxn_summary.txt), so two chains in flight per CTA (x 2 CTAs per SM) is what pays.
+        // per-thread constants of the tile loop are made opaque (keep_*): left transparent, ptxas re-derives them from
+        // SR_TID.X / SR_CgaCtaId / SR_SWINHI inside every tile (three S2R and five S2UR round trips per tile, ~8 % of the
+        // epilogue's samples on d1.1 in profiles/r01_ncu_v14_igemm_all_launches.txt) instead of keeping seven registers
         const int quarter = warp & 3;
         const int grp = (warp - 2) >> 2;
-        const int row = quarter * 32 + lane;
-        const int etid = (threadIdx.x - 64) & 127;              // 0..127 inside the group
-        const int ty = row >> P.tw_shift;
-        const int tx = row & (P.TW - 1);
+        const int lane = ptx::keep_i32((int)(threadIdx.x & 31));
+        const int row = ptx::keep_i32(quarter * 32 + lane);
+        const int etid = ptx::keep_i32((int)((threadIdx.x - 64) & 127));   // 0..127 inside the group
+        const int ty = ptx::keep_i32(row >> P.tw_shift);
+        const int tx = ptx::keep_i32(row & (P.TW - 1));
         constexpr int f16 = F16 ? 1 : 0;
         const int c_pitch = P.CB * 2;                           // bytes per staged row == store swizzle width
         const uint32_t swz_mask = (uint32_t)(c_pitch >> 4) - 1; // 7 / 3 / 1 for 128 / 64 / 32-byte swizzle
@@ -637,13 +641,15 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         uint32_t acc_phase = 0;
         uint32_t c_phase = 0;
         int cslot = 0;                                          // this group's two staging tiles alternate per TMA store
-        uint8_t* cs = smem_c + (size_t)(grp * P.cslots) * P.c_slot_bytes;
-        uint8_t* ps = smem_p + (size_t)(grp * P.cslots) * P.p_slot_bytes;
+        const uint32_t smem_c_u32 = ptx::keep_u32(ptx::smem_u32(smem_c)), smem_p_u32 = ptx::keep_u32(ptx::smem_u32(smem_p));
+        const uint32_t c_grp = smem_c_u32 + (uint32_t)(grp * P.cslots * P.c_slot_bytes);   // this group's staging tiles
+        const uint32_t p_grp = smem_p_u32 + (uint32_t)(grp * P.cslots * P.p_slot_bytes);
+        uint32_t cs = c_grp, ps = p_grp;                        // current staging tile / pooled staging tile (shared addresses)
 #define NEXT_CSLOT()                                                                   \
     do {                                                                               \
         cslot = (cslot + 1 == P.cslots) ? 0 : cslot + 1;                               \
-        cs = smem_c + (size_t)(grp * P.cslots + cslot) * P.c_slot_bytes;               \
-        ps = smem_p + (size_t)(grp * P.cslots + cslot) * P.p_slot_bytes;               \
+        cs = c_grp + (uint32_t)(cslot * P.c_slot_bytes);                               \
+        ps = p_grp + (uint32_t)(cslot * P.p_slot_bytes);                               \
     } while (0)
 #define WAIT_STORE_READS()                                                             \
     do {                                                                               \
@@ -651,7 +657,9 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         else                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); \
     } while (0)
         int par = 1;                                            // parity of this group's tile iteration
-        uint64_t* cbar = &c_load_bar[grp];
+        const uint32_t cbar = ptx::keep_u32(ptx::smem_u32(&c_load_bar[grp]));
+        const uint32_t full_bar = ptx::keep_u32(ptx::smem_u32(&tmem_full_bar[acc]));
+        const uint32_t empty_bar = ptx::keep_u32(PAIR ? (ptx::smem_u32(&tmem_empty_bar[acc]) & ptx::kPeerBitMask) : ptx::smem_u32(&tmem_empty_bar[acc]));
         // the bias slice of a CTA never changes when there is one problem, no per-image bias and one N tile per CTA:
         // it is staged once instead of once per tile
         const bool bias_static = P.nprob == 1 && P.prob[0].bias_img_stride == 0 && (P.prob[0].n_tiles == 1 || P.b_resident != 0);
@@ -663,7 +671,6 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout
                                           : q0.epi == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
         }
-        const uint32_t smem_c_u32 = ptx::smem_u32(smem_c), smem_p_u32 = ptx::smem_u32(smem_p);
         // The barrier at the top of a tile publishes the tile's bias and the "staging tile is free again" news.  With a
         // static bias it can go when nothing is staged (OUTCONV), or when tiles are single-chunk STOREs alternating
         // between two staging tiles: there thread 0 waits for the PREVIOUS tile's store to have read its tile right
@@ -710,7 +717,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             TM_MARK(0);                                         // 0: tile bookkeeping
             if (etid == 0 && !skip_top_bar) WAIT_STORE_READS(); // the store that last used the next staging tile has left smem
             TM_MARK(1);                                         // 1: wait for the previous TMA store to have read its tile
-            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, P.err, ERR_EPI_WAIT);
+            ptx::mbar_wait(full_bar, acc_phase, P.err, ERR_EPI_WAIT);
             acc_phase ^= 1;
             ptx::tc_fence_after();
             TM_MARK(2);                                         // 2: wait for the accumulator
@@ -752,7 +759,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                                            pack2(f[v * 8 + 4], f[v * 8 + 5], f16), pack2(f[v * 8 + 6], f[v * 8 + 7], f16));
                                 uint32_t off = (uint32_t)(srow * c_pitch + (c0 + v * 8) * 2);
                                 off ^= ((off >> 7) & swz_mask) << 4;
-                                sts128(ptx::smem_u32(cs) + off, o);
+                                sts128(cs + off, o);
                             }
                         }
                     } else {
@@ -768,22 +775,22 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
+                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
                 if (q.epi == EPI_STORE) {
                     if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
                     if (P.pool) {
-                        pool_staged_tile(ptx::smem_u32(cs), ptx::smem_u32(ps), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                        pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                     }
                     if (etid == 0) {
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(tc.n0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
+                                     ::"l"((uint64_t)&P.tmC[0]), "r"(cs), "r"(tc.n0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
                         if (P.pool)
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                         ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(ps)), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
+                                         ::"l"((uint64_t)&P.tmP), "r"(ps), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     NEXT_CSLOT();
@@ -795,17 +802,17 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
               // whole accumulator is converted first and fence / barrier / TMA stores happen ONCE per tile; otherwise the
               // chunks rotate through `cslots` tiles with a barrier pair per chunk.
               const bool batch = P.cbatch != 0;
-              auto issue_store = [&](const uint8_t* c_tile, const uint8_t* p_tile, int mb, int c0) {
+              auto issue_store = [&](uint32_t c_tile, uint32_t p_tile, int mb, int c0) {
                   const int n = tc.n0 + c0, yb = tc.y0 + mb * P.TH;
                   const void* tm;
                   int cch;
                   if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
                   else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                               ::"l"((uint64_t)tm), "r"(ptx::smem_u32(c_tile)), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
+                               ::"l"((uint64_t)tm), "r"(c_tile), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
                   if (P.pool)
                       asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                   ::"l"((uint64_t)&P.tmP), "r"(ptx::smem_u32(p_tile)), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
+                                   ::"l"((uint64_t)&P.tmP), "r"(p_tile), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
               };
               for (int mb = 0; mb < P.MT; ++mb) {                               // M-blocks of the tile (vertically stacked)
                 taddr = taddr0 + (uint32_t)(mb * P.BN);
@@ -819,7 +826,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         // 4..6 with bits 7..9, and a staged row never crosses a 128-byte line, so xr is per thread
                         const uint32_t row_base = (uint32_t)(srow * c_pitch);
                         const uint32_t xr = ((row_base >> 7) & swz_mask) << 4;
-                        const uint32_t cs_row = smem_c_u32 + (uint32_t)((grp * P.cslots + cslot) * P.c_slot_bytes) + row_base;
+                        const uint32_t cs_row = cs + row_base;
                         const bool relu = q.relu != 0;
                         auto convert8 = [&](const uint32_t* r8, int col) {           // 8 accumulator columns -> one 16-byte vector
                             const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + col);
@@ -851,7 +858,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (c0 + P.CB >= P.BN && mb == P.MT - 1) {                // accumulator fully read: free the TMEM stage
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
+                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
                     }
                     TM_MARK(4);                                                 // 4: TMEM -> registers -> staged tile
                     if (!batch) {
@@ -860,7 +867,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         EPI_BAR();
                         TM_MARK(5);                                             // 5: proxy fence + barrier
                         if (P.pool) {
-                            pool_staged_tile(ptx::smem_u32(cs), ptx::smem_u32(ps), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                            pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             EPI_BAR();
                             TM_MARK(6);                                         // 6: pooling + fence + barrier
@@ -877,11 +884,9 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
               if (batch) {                                                      // cslot is back at 0: chunk j sits in staging tile j
                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                   EPI_BAR();
-                  uint8_t* c_base = smem_c + (size_t)(grp * P.cslots) * P.c_slot_bytes;
-                  uint8_t* p_base = smem_p + (size_t)(grp * P.cslots) * P.p_slot_bytes;
                   if (P.pool) {
                       for (int j = 0; j < P.cslots; ++j)
-                          pool_staged_tile(ptx::smem_u32(c_base) + (uint32_t)(j * P.c_slot_bytes), ptx::smem_u32(p_base) + (uint32_t)(j * P.p_slot_bytes), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
+                          pool_staged_tile(c_grp + (uint32_t)(j * P.c_slot_bytes), p_grp + (uint32_t)(j * P.p_slot_bytes), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                       EPI_BAR();
                   }
@@ -889,7 +894,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                       int j = 0;
                       for (int mb = 0; mb < P.MT; ++mb)
                           for (int c0 = 0; c0 < P.BN; c0 += P.CB, ++j)
-                              issue_store(c_base + (size_t)j * P.c_slot_bytes, p_base + (size_t)j * P.p_slot_bytes, mb, c0);
+                              issue_store(c_grp + (uint32_t)(j * P.c_slot_bytes), p_grp + (uint32_t)(j * P.p_slot_bytes), mb, c0);
                       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
               }
@@ -908,7 +913,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 const uint32_t row_base = (uint32_t)(srow * c_pitch);
                 const uint32_t xr = ((row_base >> 7) & swz_mask) << 4;
-                const uint32_t slot0 = smem_c_u32 + (uint32_t)(grp * P.cslots * P.c_slot_bytes);
+                const uint32_t slot0 = c_grp;
                 for (int c0 = 0; c0 < CC; c0 += P.CB) {
                     if (c0 > 0) {                                               // both staging tiles are reused per chunk
                         if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -939,7 +944,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (c0 + P.CB >= CC) {                                      // accumulator fully read: free the TMEM stage
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
+                        if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
@@ -972,7 +977,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[acc]); else ptx::mbar_arrive(&tmem_empty_bar[acc]); }
+                if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
                 if (q.epi == EPI_OUTCONV) {
                     if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 } else {
@@ -992,19 +997,19 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         for (int v = 0; v < (c_pitch >> 4); ++v) {
                             uint32_t off = (uint32_t)(row * c_pitch + v * 16);
                             off ^= ((off >> 7) & swz_mask) << 4;
-                            uint4 val = *reinterpret_cast<uint4*>(cs + off);
+                            uint4 val = lds128(cs + off);
                             const float2 p0 = unpack2(val.x, f16), p1 = unpack2(val.y, f16), p2 = unpack2(val.z, f16), p3 = unpack2(val.w, f16);
                             val.x = pack2(p0.x * scale, p0.y * scale, f16);
                             val.y = pack2(p1.x * scale, p1.y * scale, f16);
                             val.z = pack2(p2.x * scale, p2.y * scale, f16);
                             val.w = pack2(p3.x * scale, p3.y * scale, f16);
-                            *reinterpret_cast<uint4*>(cs + off) = val;
+                            sts128(cs + off, val);
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                         if (etid == 0) {
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                         ::"l"((uint64_t)&P.tmC[0]), "r"(ptx::smem_u32(cs)), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
+                                         ::"l"((uint64_t)&P.tmC[0]), "r"(cs), "r"(c0), "r"(tc.x0), "r"(tc.y0), "r"(tc.b) : "memory");
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         NEXT_CSLOT();
