@@ -9,6 +9,7 @@
 // Reference graph being reproduced: attention_aspp_unet_pipeline_stage.py:111-127 (and test_ablation.py:168-218).
 #include "../../include/aau.h"
 #include "hbm_kernels.cuh"
+#include "stem_tc.cuh"
 
 #include <cudaTypedefs.h>
 #include <algorithm>
@@ -113,6 +114,7 @@ struct Engine {
     bool committed = false;
     std::map<std::string, GemmW> gw;                  // by layer name
     float *d_stem_w = nullptr, *d_stem_b = nullptr;   // [9][c], [c]
+    uint16_t* d_stem_wB = nullptr;                     // [c][16] K-major, w*s/255 in the activation type (tensor-core stem)
     float *d_poolT = nullptr, *d_poolb = nullptr, *d_projT = nullptr, *d_projb = nullptr;
     std::vector<void*> dev_allocs;
     std::vector<std::unique_ptr<Plan>> plans;
@@ -125,6 +127,7 @@ struct Engine {
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
     int opt_pair = 1;
+    int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
     int last_launches = 0;
@@ -357,6 +360,12 @@ static int commit_weights(Engine& e) {
             }
             if (upload(e, w9c, &e.d_stem_w) != cudaSuccess || upload(e, b, &e.d_stem_b) != cudaSuccess)
                 return e.fail(AAU_ERR_CUDA, "stem upload failed");
+            // tensor-core stem: the A operand holds raw pixel values 0..255 (exact in bf16 / fp16), so 1/255 goes here
+            std::vector<uint16_t> wB((size_t)c * 16, 0);
+            for (int o = 0; o < c; ++o)
+                for (int tp = 0; tp < 9; ++tp)
+                    wB[(size_t)o * 16 + tp] = to16((float)((double)(*w)[(size_t)o * 9 + tp] * s[o] / 255.0), e.is_fp16());
+            if (upload(e, wB, &e.d_stem_wB) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "stem upload failed");
         }
     }
     if ((r = prep_conv_bn(e, P, "d1.1", "d1.1.block.0.weight", "d1.1.block.1", c, c, 9))) return r;
@@ -979,13 +988,46 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         const int twc = std::min(256 / (c / 8), (int)STEM_MAX_TW);
         const int tiles_x = (W + twc - 1) / twc, tiles_y = (H + STEM_TR - 1) / STEM_TR;
         const int grid = (int)std::min<long long>((long long)B * tiles_x * tiles_y, (long long)e.num_sms * 2 * 4);
+        // uint8 frames (the sweep path) go through the tensor-core stem; float frames keep the packed-fp32 kernel,
+        // whose arithmetic does not round the input
+        const bool tc_ok = e.opt_stem_tc != 0 && (c == 16 || c == 32 || c == 48) && (long long)B * H * W < (1ll << 31) - 512 && e.d_stem_wB != nullptr;
+        StemTcParams SP;
+        memset(&SP, 0, sizeof(SP));
+        int tc_grid = 0;
+        size_t tc_smem = 0;
+        if (tc_ok) {
+            SP.CB = c % 32 == 0 ? 32 : 16;
+            const uint64_t cdims[2] = {(uint64_t)c, (uint64_t)B * H * W};
+            const uint64_t cstr[1] = {(uint64_t)o.ld * 2};
+            const uint32_t cbox[2] = {(uint32_t)SP.CB, 128u};
+            if (!encode_map(e, &SP.tmC, o.p + (size_t)o.choff * 2, 2, cdims, cstr, cbox, SP.CB * 2))
+                return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem output");
+            SP.wB = e.d_stem_wB; SP.bias = b; SP.err = e.d_err;
+            SP.P = (uint32_t)((long long)B * H * W);
+            SP.H = H; SP.W = W; SP.C = c;
+            SP.fdW = make_fastdiv((uint32_t)W); SP.fdH = make_fastdiv((uint32_t)H);
+            SP.n_macro = (int)((SP.P + 511u) / 512u);
+            SP.tmem_cols = 32;
+            while (SP.tmem_cols < 2 * STEM_TC_SUB * c) SP.tmem_cols <<= 1;
+            SP.is_fp16 = f16 ? 1 : 0;
+            tc_smem = stem_tc_smem_bytes(c);
+            const int per_sm = (2 * SP.tmem_cols <= 512 && 2 * (tc_smem + 2048) <= 232448) ? 2 : 1;
+            tc_grid = std::min(SP.n_macro, e.num_sms * per_sm);
+        }
         OpInfo oi;
         oi.name = "d1.0";
-        oi.kernel = "stem_conv3x3_kernel";
+        oi.kernel = tc_ok ? "stem_tc_kernel" : "stem_conv3x3_kernel";
         oi.flops = 2.0 * B * H * W * 9 * c;
         oi.bytes = (double)B * H * W * (4 + 2.0 * c);     // fp32 frame in (1 byte when uint8) + NHWC out
         plan.info.push_back(oi);
         plan.ops.push_back([=](const FwdArgs& a) -> cudaError_t {
+            if (tc_ok && a.x_dtype == AAU_X_U8) {
+                StemTcParams sp = SP;
+                sp.x = (const uint8_t*)a.x;
+                if (f16) stem_tc_kernel<true><<<tc_grid, STEM_TC_THREADS, tc_smem, a.stream>>>(sp);
+                else     stem_tc_kernel<false><<<tc_grid, STEM_TC_THREADS, tc_smem, a.stream>>>(sp);
+                return cudaGetLastError();
+            }
             if (f16) stem_conv3x3_kernel<true><<<grid, 256, 0, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, tiles_x, tiles_y);
             else     stem_conv3x3_kernel<false><<<grid, 256, 0, a.stream>>>(a.x, a.x_dtype, o.B, o.H, o.W, w, b, o.p, o.ld, o.choff, o.C, tiles_x, tiles_y);
             return cudaGetLastError();
@@ -1214,7 +1256,8 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
     if (!raise_smem((const void*)igemm_tc_kernel<2, false, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false>) ||
         !raise_smem((const void*)igemm_tc_kernel<4, false, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true, false>) ||
         !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>) ||
-        !raise_smem((const void*)igemm_tc_kernel<2, false, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false, true>)) {
+        !raise_smem((const void*)igemm_tc_kernel<2, false, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false, true>) ||
+        !raise_smem((const void*)stem_tc_kernel<false>) || !raise_smem((const void*)stem_tc_kernel<true>)) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;
@@ -1524,7 +1567,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

@@ -140,7 +140,12 @@ def test_full_size_invariants():
     b = net(xu8)
     assert torch.equal(a, b)                                           # deterministic
     xf = (torch.from_numpy(vol.astype(np.float32)) / 255.0).unsqueeze(1).cuda()
-    assert torch.equal(net(xf), a)                                     # u8 ingest == float(u8)/255 (model_attention_aspp.py:17)
+    # u8 ingest == float(u8)/255 (model_attention_aspp.py:17): uint8 frames run d1.0 on the tensor cores (weights rounded
+    # to bf16 like every other layer's), float frames through the fp32 FMA stem -> equal up to that rounding ...
+    assert (net(xf) - a).abs().mean().item() < 0.02 * a.std().item()
+    net.set_option("stem_tc", 0)                                       # ... and bit-identical when both use the FMA stem
+    assert torch.equal(net(xf), net(xu8))
+    net.set_option("stem_tc", 1)
     one = torch.cat([net(xu8[i:i + 1]) for i in range(5)])
     assert torch.equal(one, a)                                         # frames are independent: batch size never changes a pixel
     perm = torch.tensor([3, 0, 4, 1, 2], device="cuda")
@@ -153,6 +158,41 @@ def test_full_size_invariants():
     assert (c - a).abs().mean().item() < 0.02 * a.std().item()
     assert torch.equal(net(xu8), a)
     net.check_device()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("c,shape", [(32, (3, 141, 93)), (16, (2, 80, 72)), (48, (1, 64, 81)), (32, (1, 17, 33)), (32, (5, 96, 128)), (32, (1, 562, 744))])
+def test_tensor_core_stem_uint8(c, shape, dtype):
+    """d1.0 as a K = 16 implicit GEMM over raw uint8 pixels (stem_tc.cuh) against the oracle's fp32 Conv+BN+ReLU of
+    frame/255, at sizes whose pixel count is / is not a multiple of the 512-pixel macro-tile, and the whole forward behind it."""
+    cfg = O.NetCfg(base_c=c)
+    B, H, W = shape
+    sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), torch.rand(2, 1, H, W, generator=torch.Generator().manual_seed(3)), cfg)
+    vol = O.synthetic_sweep(B, H, W, seed=6, peak=B // 2)
+    vol[0, 0, :] = 255; vol[0, :, 0] = 255; vol[-1, -1, :] = 255; vol[-1, :, -1] = 255     # bright image borders: padding must stay zero
+    x = torch.from_numpy(vol.astype(np.float32) / 255.0).unsqueeze(1)
+    taps = {}
+    ref = O.forward(sd, x, cfg, taps=taps)
+    net = make_net(cfg, sd, dtype)
+    out = net(torch.from_numpy(vol).cuda()).cpu()
+    net.check_device()
+    got, want = net.debug_tensor("d1.0").cpu(), taps["d1.0"]
+    assert got.shape == want.shape
+    # one 16-bit rounding of the weights and one of the output (bf16: 8 significant bits, fp16: 11)
+    tol = (2.0 ** -7 if dtype == "bf16" else 2.0 ** -10) * want.abs().max().item() + 1e-3
+    assert (got - want).abs().max().item() <= tol, (got - want).abs().max().item()
+    assert ((got - want).abs().mean() / want.abs().mean()).item() < (5e-3 if dtype == "bf16" else 1e-3)
+    net.set_option("stem_tc", 0)
+    fma = net(torch.from_numpy(vol).cuda()).cpu()
+    spread = ref.std().item()
+    for other in (ref, fma):                                            # bf16 storage noise of 30 layers vs fp16's
+        d = (out - other).abs()
+        assert d.mean().item() <= (0.04 if dtype == "bf16" else 0.004) * spread + 1e-3
+        assert d.max().item() <= (0.3 if dtype == "bf16" else 0.03) * spread + 2e-2
+    # masks: random-weight logits crowd the threshold, so bf16 storage alone flips ~1 % of the pixels; the tensor-core
+    # stem must not flip more than the FMA stem does
+    assert agreement(out, ref, 0.5) >= (0.985 if dtype == "bf16" else 0.995)
+    assert agreement(out, ref, 0.5) >= agreement(fma, ref, 0.5) - 0.004
 
 
 def test_small_and_ragged_sizes():
@@ -242,8 +282,8 @@ OPTION_SETS = [
     {"ng": 2, "ctas": 1, "cslots": 1},
     {"resident": 0},                # weights streamed through the B ring
     {"titer": 0, "pdl": 0, "side": 0, "fusepool": 0},
-    {"pair": 0, "lean": 0, "convt_batch": 0},
-    {"dxn_full": 0},                            # u2.conv.0 with its dx-stacked weights split in two N tiles   # no CTA pairs (cta_group::2), per-tile top barrier everywhere, per-chunk transposed-conv sync
+    {"pair": 0, "lean": 0, "convt_batch": 0},   # no CTA pairs (cta_group::2), per-tile top barrier everywhere, per-chunk transposed-conv sync
+    {"dxn_full": 0},                # u2.conv.0 with its dx-stacked weights split in two N tiles
 ]
 
 
