@@ -1024,6 +1024,7 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             if (tc_ok && a.x_dtype == AAU_X_U8) {
                 StemTcParams sp = SP;
                 sp.x = (const uint8_t*)a.x;
+                sp.x_aligned = ((uintptr_t)a.x & 15) == 0 ? 1 : 0;
                 if (f16) stem_tc_kernel<true><<<tc_grid, STEM_TC_THREADS, tc_smem, a.stream>>>(sp);
                 else     stem_tc_kernel<false><<<tc_grid, STEM_TC_THREADS, tc_smem, a.stream>>>(sp);
                 return cudaGetLastError();

@@ -9,16 +9,21 @@
 // 16-byte shared stores per pixel.
 //
 // Pixels are taken in linear order over the whole batch (p = (b*H + y)*W + x), 512 per macro-tile, so there is no
-// tile padding at row / image ends; taps outside the image are masked to zero per pixel.  Roles of a CTA (416 threads,
+// tile padding at row / image ends; taps outside the image are masked to zero per pixel.  Roles of a CTA (448 threads,
 // two CTAs per SM): warp 0 = TMEM owner + MMA issuer, warps 1-4 = im2col builders (one pixel row of the A tile per
 // thread and 128-pixel sub-tile), warps 5-12 = two epilogue groups (group g drains accumulator stage g: tcgen05.ld ->
-// bias, ReLU, 16-bit pack -> swizzled staging -> one TMA store per sub-tile).
+// bias, ReLU, 16-bit pack -> swizzled staging -> one TMA store per sub-tile), warp 13 = input producer: the three
+// 514-byte row segments a macro-tile reads (rows y-1, y, y+1 in linear pixel order) arrive in a four-slot shared-memory
+// ring by cp.async.bulk, several macro-tiles ahead -- read straight from global memory the builders spent 57 % of their
+// time in load latency (ncu source view, profiles/r01_ncu_stem_tc.txt).  Macro-tiles whose segments would start
+// before the buffer or end after it (the first and last few) keep the masked global loads.
 #pragma once
 #include "igemm_tc.cuh"
 
 namespace aau {
 
-constexpr int STEM_TC_THREADS = 32 + 128 + 256;
+constexpr int STEM_TC_THREADS = 32 + 128 + 256 + 32;
+constexpr int STEM_IN_SLOTS = 4, STEM_SEG_BYTES = 544, STEM_IN_SLOT_BYTES = 3 * STEM_SEG_BYTES;   // 512 + 2 pixels + 16-byte alignment slack
 constexpr int STEM_TC_SUB = 4;                       // 128-pixel sub-tiles (MMAs) per macro-tile
 enum { ERR_STEM_BUILD_WAIT = 111, ERR_STEM_MMA_WAIT = 112, ERR_STEM_EPI_WAIT = 113 };
 
@@ -34,16 +39,23 @@ struct StemTcParams {
     int n_macro;            // ceil(P / 512)
     int tmem_cols;          // power of two >= 2 * STEM_TC_SUB * C
     int is_fp16;
+    int x_aligned;          // x is 16-byte aligned (cp.async.bulk source)
 };
 
 static inline size_t stem_tc_smem_bytes(int C) {
-    return 1024 /*align*/ + 2 * STEM_TC_SUB * 4096 /*A*/ + 2048 /*B*/ + 2 * STEM_TC_SUB * 128 * C * 2 /*staging*/;
+    return 1024 /*align*/ + 2 * STEM_TC_SUB * 4096 /*A*/ + 2048 /*B*/ + 2 * STEM_TC_SUB * 128 * C * 2 /*staging*/ + STEM_IN_SLOTS * STEM_IN_SLOT_BYTES /*input ring*/;
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 template <bool F16>
 __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ StemTcParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], in_full[STEM_IN_SLOTS], in_empty[STEM_IN_SLOTS];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[64];
 
@@ -54,6 +66,12 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
     const uint32_t smem_b = smem_a + 2 * STEM_TC_SUB * 4096;            // [C rows][32 B], same swizzle
     const uint32_t smem_c = smem_b + 2048;                              // [group][sub][chunk][128 rows][CB*2 B]
     const int C = P.C;
+    const uint32_t smem_in = smem_c + (uint32_t)(2 * STEM_TC_SUB * 128 * C * 2);   // [slot][row -1, 0, +1][544 B]
+    // a macro-tile is "fast" when its three row segments, widened to 16-byte alignment, lie inside the pixel buffer
+    auto fast_tile = [&](int m) -> bool {
+        const uint32_t p0 = (uint32_t)m * 512u;
+        return P.x_aligned != 0 && p0 >= (uint32_t)P.W + 16u && (unsigned long long)p0 + (unsigned)P.W + STEM_SEG_BYTES <= (unsigned long long)P.P;
+    };
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&P.tmC);
@@ -63,6 +81,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
             ptx::mbar_init(&t_full[s], 1);
             ptx::mbar_init(&t_empty[s], 4);
         }
+        for (int s = 0; s < STEM_IN_SLOTS; ++s) { ptx::mbar_init(&in_full[s], 1); ptx::mbar_init(&in_empty[s], 128); }
         ptx::fence_mbar_init();
     }
     if (warp == 0) {
@@ -111,17 +130,42 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
         const uint32_t sw = (uint32_t)((t >> 2) & 1) << 4;
         const int W = P.W, H = P.H;
         int i = 0;
+        uint32_t nf = 0;                                                // fast macro-tiles so far = uses of the input ring
         for (int m = blockIdx.x; m < P.n_macro; m += gridDim.x, ++i) {
             const int s = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             ptx::mbar_wait(&a_empty[s], ph ^ 1u, P.err, ERR_STEM_BUILD_WAIT);
+            const bool fast = fast_tile(m);
+            uint32_t seg[3] = {0u, 0u, 0u};                             // shared address of this thread's centre byte per row
+            const uint32_t slot = nf & (STEM_IN_SLOTS - 1);
+            if (fast) {
+                ptx::mbar_wait(&in_full[slot], (nf >> 2) & 1u, P.err, ERR_STEM_BUILD_WAIT);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t s0 = (uint32_t)m * 512u + (uint32_t)((k - 1) * W) - 1u;      // first byte the segment needs
+                    seg[k] = smem_in + slot * STEM_IN_SLOT_BYTES + (uint32_t)(k * STEM_SEG_BYTES) + (s0 & 15u) + 1u + (uint32_t)t;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < STEM_TC_SUB; ++j) {
                 const uint32_t p = (uint32_t)m * 512u + (uint32_t)(j * 128 + t);
                 uint32_t v[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) v[k] = 0;
-                if (p < P.P) {
+                if (fast) {
+                    const uint32_t q = fdiv(p, P.fdW);                  // b*H + y
+                    const int x = (int)(p - q * (uint32_t)W);
+                    const int y = (int)(q - fdiv(q, P.fdH) * (uint32_t)H);
+                    const uint32_t mrow[3] = {y > 0 ? 0xffu : 0u, 0xffu, y < H - 1 ? 0xffu : 0u};
+                    const uint32_t ml = x > 0 ? 0xffu : 0u, mr = x < W - 1 ? 0xffu : 0u;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t a = seg[k] + (uint32_t)(j * 128);
+                        v[k * 3 + 0] = lds_u8(a - 1u) & mrow[k] & ml;
+                        v[k * 3 + 1] = lds_u8(a) & mrow[k];
+                        v[k * 3 + 2] = lds_u8(a + 1u) & mrow[k] & mr;
+                    }
+                } else if (p < P.P) {
                     const uint32_t q = fdiv(p, P.fdW);                  // b*H + y
                     const int x = (int)(p - q * (uint32_t)W);
                     const int y = (int)(q - fdiv(q, P.fdH) * (uint32_t)H);
@@ -145,8 +189,29 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
                 sts128(base + sw, lo);
                 sts128(base + (sw ^ 16u), hi);
             }
+            if (fast) { ptx::mbar_arrive(&in_empty[slot]); ++nf; }        // this thread is done with the input slot
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async reads
             ptx::mbar_arrive(&a_full[s]);
+        }
+    } else if (warp == 13) {
+        // =========================== input producer ===========================
+        uint32_t nf = 0;
+        for (int m = blockIdx.x; m < P.n_macro; m += gridDim.x) {
+            if (!fast_tile(m)) continue;
+            const uint32_t slot = nf & (STEM_IN_SLOTS - 1);
+            ptx::mbar_wait(&in_empty[slot], ((nf >> 2) & 1u) ^ 1u, P.err, ERR_STEM_BUILD_WAIT);
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(&in_full[slot], (uint32_t)STEM_IN_SLOT_BYTES);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t s0 = (uint32_t)m * 512u + (uint32_t)((k - 1) * P.W) - 1u;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_in + slot * STEM_IN_SLOT_BYTES + (uint32_t)(k * STEM_SEG_BYTES)), "l"(P.x + (s0 & ~15u)),
+                                   "r"((uint32_t)STEM_SEG_BYTES), "r"(ptx::smem_u32(&in_full[slot])) : "memory");
+                }
+            }
+            __syncwarp();
+            ++nf;
         }
     } else {
         // =========================== epilogue groups ===========================
