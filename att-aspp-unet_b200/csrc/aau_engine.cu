@@ -126,7 +126,7 @@ struct Engine {
     int opt_fusefix = 1;
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
-    int opt_pair = 1;
+    int opt_pair = 3;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
@@ -684,8 +684,12 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     const int steps = (dxn ? 3 : d0.w->taps) * nchunk;            // k-steps (one B sub-block each) per tile
     // CTA pairs (cta_group::2): slab-staged layers whose weights stream, one N tile, an even number of tiles
     const int tiles_total0 = d0.in.B * ((W + P.VW - 1) / P.VW) * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
-    const bool pair = e.opt_pair != 0 && slab && !dxn && !rs && descs.size() == 1 && d0.epi == EPI_STORE && Ntot == BN && BN >= 128 &&
-                      (size_t)9 * Cin * BN * 2 > 112 * 1024 && tiles_total0 % 2 == 0 && tiles_total0 >= 2;
+    const bool pair_slab = (e.opt_pair & 1) != 0 && slab && !dxn && !rs && descs.size() == 1 && (size_t)9 * Cin * BN * 2 > 112 * 1024;
+    // ... and per-tap staged STORE layers with streamed weights (the dilated ASPP branches as one three-problem launch,
+    // the ASPP projection): every problem has an even number of tiles, so the two CTAs of a pair stay on one problem
+    const bool pair_tap = (e.opt_pair & 2) != 0 && !slab && !cfix && (descs.size() > 1 || (size_t)d0.w->taps * Cin * BN * 2 > 112 * 1024);
+    const bool pair = (pair_slab || pair_tap) && d0.epi == EPI_STORE && (Ntot == BN || pair_tap) && BN >= 128 && tiles_total0 % 2 == 0 && tiles_total0 >= 2;
+    P.pair_order = (pair && Ntot != BN) ? 1 : 0;                  // several N tiles: a pair walks two M tiles of one N tile
     P.b_slot_bytes = (pair ? BN / 2 : BN) * swz;
     P.a_slot_bytes = slab ? (((P.TH * P.MT + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
     // epilogue staging: channels per TMA store (the store swizzle width is CB*2 bytes)
@@ -896,6 +900,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
+        if (pair && Q.nprob > 1) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true, true>, Q);
         if (pair) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, false, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, false, true>, Q);
         if (Q.nprob > 1)                                               // several problems per launch: always 2 groups (BN = 256)
             return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true>, Q);
@@ -1258,6 +1263,7 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         !raise_smem((const void*)igemm_tc_kernel<4, false, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true, false>) ||
         !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>) ||
         !raise_smem((const void*)igemm_tc_kernel<2, false, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false, true>) ||
+        !raise_smem((const void*)igemm_tc_kernel<2, false, true, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true, true>) ||
         !raise_smem((const void*)stem_tc_kernel<false>) || !raise_smem((const void*)stem_tc_kernel<true>)) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;

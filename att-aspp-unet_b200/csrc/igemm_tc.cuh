@@ -146,6 +146,7 @@ struct alignas(64) IgemmParams {
     int is_fp16;
     int lean_sync;          // 1: drop the per-tile top barrier where a static bias and alternating staging tiles allow it
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
+    int pair_order;         // CTA pairs over several N tiles: consecutive tiles are two M tiles of one N tile
     int* err;
 };
 
@@ -202,8 +203,14 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
         if (i < P.nprob && t >= P.prob[i].tile_begin) pi = i;
     const IgemmProblem& q = P.prob[pi];
     const int local = t - q.tile_begin;
-    const int mt = (int)fdiv((uint32_t)local, q.fd_n_tiles);
-    const int nt = local - mt * q.n_tiles;
+    int mt = (int)fdiv((uint32_t)local, q.fd_n_tiles);
+    int nt = local - mt * q.n_tiles;
+    if (P.pair_order) {                                           // CTA pairs with several N tiles: tiles 2k, 2k+1 = M tiles 2j, 2j+1 of ONE N tile
+        const int k = local >> 1;
+        const int j = (int)fdiv((uint32_t)k, q.fd_n_tiles);
+        nt = k - j * q.n_tiles;
+        mt = 2 * j + (local & 1);
+    }
     tc.pi = pi;
     tc.b = (int)fdiv((uint32_t)mt, q.fd_tiles_per_img);
     const int r = mt - tc.b * q.tiles_per_img;
@@ -227,7 +234,7 @@ struct TileIter {
     bool incremental;
     __device__ __forceinline__ void init(const IgemmParams& P, int first, int stride_) {
         t = first; stride = stride_; total = P.total_tiles;
-        incremental = P.nprob == 1 && P.tile_iter != 0;
+        incremental = P.nprob == 1 && P.tile_iter != 0 && P.pair_order == 0;
         if (incremental) {
             const IgemmProblem& q = P.prob[0];
             tiles_x = q.tiles_x; n_tiles = q.n_tiles;
@@ -294,6 +301,12 @@ __device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int t
         }
 }
 
+__device__ __forceinline__ void tap_offsets(const IgemmProblem& q, int tap, int& dy, int& dx) {
+    dy = 0; dx = 0;
+    if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
+    else if (q.taps == 2) { dy = q.fix_axis == 0 ? tap - 1 : 0; dx = q.fix_axis == 1 ? tap - 1 : 0; }
+}
+
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
 // field, so stepping K by 32 bytes is "+2" on the low word.
 template <int KK, bool PAIR = false>
@@ -354,9 +367,9 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    mma_subblock<KK>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                    ptx::umma_commit(&empty_a[ia]);
-                    if (!res) ptx::umma_commit(&empty_b[ib]);
+                    mma_subblock<KK, PAIR>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
+                    if (PAIR) { ptx::umma_commit_pair(&empty_a[ia]); if (!res) ptx::umma_commit_pair(&empty_b[ib]); }
+                    else      { ptx::umma_commit(&empty_a[ia]); if (!res) ptx::umma_commit(&empty_b[ib]); }
                 }
                 __syncwarp();
                 accumulate = 1;
@@ -549,17 +562,26 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     for (int s = 0; s < steps; ++s) {
                         const int tap = s / q.nchunk;
                         const int ch = s - tap * q.nchunk;
-                        int dy = 0, dx = 0;
-                        if (q.taps == 9) { dy = (tap / 3 - 1) * q.dil; dx = (tap % 3 - 1) * q.dil; }
-                        else if (q.taps == 2) { dy = q.fix_axis == 0 ? tap - 1 : 0; dx = q.fix_axis == 1 ? tap - 1 : 0; }
+                        int dy, dx;
+                        tap_offsets(q, tap, dy, dx);
                         ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (!res) ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (ptx::elect_one()) {
-                            ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
-                            ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
-                            if (!res) {
-                                ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
-                                ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC, tc.n0);
+                            if (PAIR) {                                       // both CTAs' boxes complete the LEADER's barriers
+                                if (pair_rank == 0) {
+                                    ptx::mbar_expect_tx(&full_a[ia], 2 * (uint32_t)P.a_slot_bytes);
+                                    ptx::mbar_expect_tx(&full_b[ib], 2 * (uint32_t)P.b_slot_bytes);
+                                }
+                                ptx::tma_load_4d_pair(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
+                                ptx::tma_load_2d_pair(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC,
+                                                      tc.n0 + (int)pair_rank * (P.BN / 2));      // this CTA's half of the weight rows
+                            } else {
+                                ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
+                                ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
+                                if (!res) {
+                                    ptx::mbar_expect_tx(&full_b[ib], (uint32_t)P.b_slot_bytes);
+                                    ptx::tma_load_2d(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC, tc.n0);
+                                }
                             }
                         }
                         __syncwarp();
