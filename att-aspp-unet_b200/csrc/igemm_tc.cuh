@@ -329,9 +329,14 @@ __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uin
 // vector to uniform registers first (R2UR): ~70-100 cycles per MMA instead of the 40-48 cycle hardware floor of
 // the small-N layers (profiles/r01_mma_probe.txt).
 template <int KK, bool MULTI, bool PAIR>
-__device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a, uint64_t* empty_a,
-                                         uint64_t* full_b, uint64_t* empty_b, uint64_t* b_res_bar, uint64_t* tmem_full_bar,
-                                         uint64_t* tmem_empty_bar, uint32_t tmem_base) {
+__device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a_p, uint64_t* empty_a_p,
+                                         uint64_t* full_b_p, uint64_t* empty_b_p, uint64_t* b_res_bar, uint64_t* tmem_full_p,
+                                         uint64_t* tmem_empty_p, uint32_t tmem_base) {
+    // barrier addresses once, opaque, as 32-bit shared addresses (slot s = base + 8 s): formed at each use they cost an
+    // S2UR SR_CgaCtaId + three dependent uniform ops in front of every wait / commit of this serial instruction stream
+    const uint32_t full_a = ptx::keep_u32(ptx::smem_u32(full_a_p)), empty_a = ptx::keep_u32(ptx::smem_u32(empty_a_p));
+    const uint32_t full_b = ptx::keep_u32(ptx::smem_u32(full_b_p)), empty_b = ptx::keep_u32(ptx::smem_u32(empty_b_p));
+    const uint32_t tmem_full_bar = ptx::keep_u32(ptx::smem_u32(tmem_full_p)), tmem_empty_bar = ptx::keep_u32(ptx::smem_u32(tmem_empty_p));
     const int swz = P.KC * 2;
     const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 256 : 128, P.BN, P.is_fp16 != 0);   // pair: M = 256 over the two CTAs
     const uint64_t proto = ptx::make_kmajor_desc(0, swz);
@@ -354,7 +359,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         const TileCoord tc = it.coord(P);
         const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
         TM_MARK(2);
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
+        ptx::mbar_wait(tmem_empty_bar + 8u * (uint32_t)acc, acc_phase ^ 1, P.err, ERR_MMA_WAIT_TMEM);
         ptx::tc_fence_after();
         TM_MARK(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN * P.MT);
@@ -362,14 +367,14 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         if (P.amode == AMODE_TAP) {
             const int steps = q.taps * q.nchunk;
             for (int s = 0; s < steps; ++s) {
-                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 const int bslot = res ? s : ib;
-                if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
+                if (!res) ptx::mbar_wait(full_b + 8u * (uint32_t)ib, pb, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     mma_subblock<KK, PAIR>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                    if (PAIR) { ptx::umma_commit_pair(&empty_a[ia]); if (!res) ptx::umma_commit_pair(&empty_b[ib]); }
-                    else      { ptx::umma_commit(&empty_a[ia]); if (!res) ptx::umma_commit(&empty_b[ib]); }
+                    if (PAIR) { ptx::umma_commit_pair(empty_a + 8u * (uint32_t)ia); if (!res) ptx::umma_commit_pair(empty_b + 8u * (uint32_t)ib); }
+                    else      { ptx::umma_commit(empty_a + 8u * (uint32_t)ia); if (!res) ptx::umma_commit(empty_b + 8u * (uint32_t)ib); }
                 }
                 __syncwarp();
                 accumulate = 1;
@@ -380,7 +385,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             const uint32_t row16 = (uint32_t)swz >> 4;                        // one pixel row of the slab, in 16-byte units
             for (int ch = 0; ch < q.nchunk; ++ch) {
                 TM_MARK(2);
-                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
                 TM_MARK(1);
                 if (ptx::elect_one()) {
@@ -393,7 +398,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                             mma_subblock<KK>(d_tmem + P.BN, a_lo + shift + a_mb16, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
                         mma_subblock<KK>(d_tmem, a_lo + shift, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
                     }
-                    ptx::umma_commit(&empty_a[ia]);
+                    ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
                 }
                 __syncwarp();
                 TM_MARK(3);
@@ -405,7 +410,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             const int ndc = (P.amode == AMODE_SLAB ? 3 : 1) * q.nchunk;
             for (int dc = 0; dc < ndc; ++dc) {                                // SLAB: (dx, channel chunk); DXN: channel chunk
                 TM_MARK(2);
-                ptx::mbar_wait(&full_a[ia], pa, P.err, ERR_MMA_WAIT_FULL);
+                ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 TM_MARK(1);
                 const uint32_t a_lo = a_base + ia * a_slot16;
                 if (res && !PAIR) {
@@ -421,7 +426,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                                 mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
                             mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
                         }
-                        ptx::umma_commit(&empty_a[ia]);
+                        ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
                     }
                     __syncwarp();
                     step += 3;
@@ -433,7 +438,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 #pragma unroll
                 for (int dyi = 0; dyi < 3; ++dyi, ++step) {
                     const int bslot = res ? step : ib;
-                    if (!res) ptx::mbar_wait(&full_b[ib], pb, P.err, ERR_MMA_WAIT_FULL);
+                    if (!res) ptx::mbar_wait(full_b + 8u * (uint32_t)ib, pb, P.err, ERR_MMA_WAIT_FULL);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
                         if (P.MT == 2) {                                      // second M-block: TH rows further down the slab
@@ -441,8 +446,8 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                             mma_subblock<KK, PAIR>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_base + bslot * b_slot16, desc_hi, idesc, acc2);
                         }
                         mma_subblock<KK, PAIR>(d_tmem, a_lo + dyi * a_dy16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
-                        if (!res) { if (PAIR) ptx::umma_commit_pair(&empty_b[ib]); else ptx::umma_commit(&empty_b[ib]); }
-                        if (dyi == 2) { if (PAIR) ptx::umma_commit_pair(&empty_a[ia]); else ptx::umma_commit(&empty_a[ia]); }
+                        if (!res) { if (PAIR) ptx::umma_commit_pair(empty_b + 8u * (uint32_t)ib); else ptx::umma_commit(empty_b + 8u * (uint32_t)ib); }
+                        if (dyi == 2) { if (PAIR) ptx::umma_commit_pair(empty_a + 8u * (uint32_t)ia); else ptx::umma_commit(empty_a + 8u * (uint32_t)ia); }
                     }
                     __syncwarp();
                     accumulate = 1;
@@ -453,8 +458,8 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             }
         }
         if (ptx::elect_one()) {                                               // accumulator complete -> epilogue (of both CTAs of a pair)
-            if (PAIR) ptx::umma_commit_pair(&tmem_full_bar[acc]);
-            else      ptx::umma_commit(&tmem_full_bar[acc]);
+            if (PAIR) ptx::umma_commit_pair(tmem_full_bar + 8u * (uint32_t)acc);
+            else      ptx::umma_commit(tmem_full_bar + 8u * (uint32_t)acc);
         }
         __syncwarp();
         if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1; }
