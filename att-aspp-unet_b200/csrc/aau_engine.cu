@@ -126,6 +126,7 @@ struct Engine {
     int opt_fusefix = 1;
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
+    int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
     int opt_pair = 3;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
@@ -594,6 +595,29 @@ static View sub_view(const View& v, int choff, int C) {
     return s;
 }
 
+// Instantiations of igemm_tc_kernel.  The generic ones (AM = EP = -1) branch on the staging mode and epilogue at run time
+// and serve every plan; the bf16 hot path additionally gets instantiations with both fixed at compile time -- a third of
+// the code size each, so the single-warp roles miss the instruction cache less and skip the uniform mode branches.
+struct IgemmKernelKey { int ng, f16, multi, pair, am, ep; };
+#define AAU_IGEMM_GENERIC(X) \
+    X(2, false, false, false, -1, -1) X(2, true, false, false, -1, -1) X(4, false, false, false, -1, -1) X(4, true, false, false, -1, -1) \
+    X(2, false, true, false, -1, -1) X(2, true, true, false, -1, -1) X(2, false, false, true, -1, -1) X(2, true, false, true, -1, -1) \
+    X(2, false, true, true, -1, -1) X(2, true, true, true, -1, -1)
+#define AAU_IGEMM_SPECIALISED(X) \
+    X(2, false, false, false, AMODE_RS, EPI_STORE) X(4, false, false, false, AMODE_RS, EPI_STORE) X(2, false, false, false, AMODE_RS, EPI_OUTCONV) \
+    X(2, false, false, false, AMODE_DXN, EPI_STORE) X(2, false, false, true, AMODE_SLAB, EPI_STORE) \
+    X(2, false, false, false, AMODE_TAP, EPI_GATE) X(2, false, false, false, AMODE_TAP, EPI_CONVT) X(4, false, false, false, AMODE_TAP, EPI_CONVT) \
+    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX) X(2, false, false, true, AMODE_TAP, EPI_STORE) X(2, false, true, true, AMODE_TAP, EPI_STORE)
+static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep) {
+#define X(NG, F16, MULTI, PAIR, AM, EP) \
+    if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP)) return (const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP>;
+    AAU_IGEMM_SPECIALISED(X)
+    if (am != -1 || ep != -1) return igemm_kernel(ng, f16, multi, pair, -1, -1);
+    AAU_IGEMM_GENERIC(X)
+#undef X
+    return nullptr;
+}
+
 // Builds one persistent-GEMM launch over up to 4 problems sharing input geometry, BN and KC.
 static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::vector<ConvDesc>& descs,
                      int patch_aux /*0 none,1 logits,2 psi3,3 psi2*/) {
@@ -874,7 +898,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     const bool f16k = e.is_fp16();
     // programmatic dependent launch when the op before this one in the stream is a kernel (not the side-stream join)
     const bool pdl = e.opt_pdl != 0 && plan.info.size() >= 2 && plan.info[plan.info.size() - 2].kernel[0] != '(';
-    plan.ops.push_back([P, grid, smem, patch_aux, ng, f16k, pdl, pair](const FwdArgs& a) -> cudaError_t {
+    const void* fn = igemm_kernel(ng, f16k, P.nprob > 1, pair, e.opt_spec != 0 ? P.amode : -1, e.opt_spec != 0 ? d0.epi : -1);
+    if (!fn) return e.fail(AAU_ERR_INVALID, "no igemm_tc_kernel instantiation for this plan");
+    plan.ops.push_back([P, grid, smem, patch_aux, ng, pdl, pair, fn](const FwdArgs& a) -> cudaError_t {
         IgemmParams Q = P;
         if (patch_aux == 1) Q.prob[0].aux = a.logits;
         if (patch_aux == 2) Q.prob[0].aux = a.psi3;
@@ -900,12 +926,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        if (pair && Q.nprob > 1) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true, true>, Q);
-        if (pair) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, false, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, false, true>, Q);
-        if (Q.nprob > 1)                                               // several problems per launch: always 2 groups (BN = 256)
-            return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, true>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, true>, Q);
-        if (ng == 4) return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, true, false>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<4, false, false>, Q);
-        return f16k ? cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, true, false>, Q) : cudaLaunchKernelEx(&cfg, igemm_tc_kernel<2, false, false>, Q);
+        void* args[1] = {(void*)&Q};
+        return cudaLaunchKernelExC(&cfg, fn, args);
     });
     return AAU_OK;
 }
@@ -1259,12 +1281,12 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144) == cudaSuccess &&
                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     };
-    if (!raise_smem((const void*)igemm_tc_kernel<2, false, false>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false>) ||
-        !raise_smem((const void*)igemm_tc_kernel<4, false, false>) || !raise_smem((const void*)igemm_tc_kernel<4, true, false>) ||
-        !raise_smem((const void*)igemm_tc_kernel<2, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true>) ||
-        !raise_smem((const void*)igemm_tc_kernel<2, false, false, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, false, true>) ||
-        !raise_smem((const void*)igemm_tc_kernel<2, false, true, true>) || !raise_smem((const void*)igemm_tc_kernel<2, true, true, true>) ||
-        !raise_smem((const void*)stem_tc_kernel<false>) || !raise_smem((const void*)stem_tc_kernel<true>)) {
+    bool raised = raise_smem((const void*)stem_tc_kernel<false>) && raise_smem((const void*)stem_tc_kernel<true>);
+#define X(NG, F16, MULTI, PAIR, AM, EP) raised = raised && raise_smem((const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP>);
+    AAU_IGEMM_GENERIC(X)
+    AAU_IGEMM_SPECIALISED(X)
+#undef X
+    if (!raised) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
         return AAU_ERR_CUDA;
@@ -1574,7 +1596,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

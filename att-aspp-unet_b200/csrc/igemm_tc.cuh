@@ -328,7 +328,7 @@ __device__ __forceinline__ void mma_subblock(uint32_t d_tmem, uint32_t a_lo, uin
 // must assume divergence, wraps every UTCHMMA in an elect/branch "waterfall" loop and moves each descriptor from
 // vector to uniform registers first (R2UR): ~70-100 cycles per MMA instead of the 40-48 cycle hardware floor of
 // the small-N layers (profiles/r01_mma_probe.txt).
-template <int KK, bool MULTI, bool PAIR>
+template <int KK, bool MULTI, bool PAIR, int AM>
 __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full_a_p, uint64_t* empty_a_p,
                                          uint64_t* full_b_p, uint64_t* empty_b_p, uint64_t* b_res_bar, uint64_t* tmem_full_p,
                                          uint64_t* tmem_empty_p, uint32_t tmem_base) {
@@ -337,6 +337,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
     const uint32_t full_a = ptx::keep_u32(ptx::smem_u32(full_a_p)), empty_a = ptx::keep_u32(ptx::smem_u32(empty_a_p));
     const uint32_t full_b = ptx::keep_u32(ptx::smem_u32(full_b_p)), empty_b = ptx::keep_u32(ptx::smem_u32(empty_b_p));
     const uint32_t tmem_full_bar = ptx::keep_u32(ptx::smem_u32(tmem_full_p)), tmem_empty_bar = ptx::keep_u32(ptx::smem_u32(tmem_empty_p));
+    const int amode = AM >= 0 ? AM : P.amode;                              // compile-time in the specialised instantiations
     const int swz = P.KC * 2;
     const uint32_t idesc = ptx::make_idesc_f16(PAIR ? 256 : 128, P.BN, P.is_fp16 != 0);   // pair: M = 256 over the two CTAs
     const uint64_t proto = ptx::make_kmajor_desc(0, swz);
@@ -364,7 +365,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         TM_MARK(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN * P.MT);
         uint32_t accumulate = 0;
-        if (P.amode == AMODE_TAP) {
+        if (amode == AMODE_TAP) {
             const int steps = q.taps * q.nchunk;
             for (int s = 0; s < steps; ++s) {
                 ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
@@ -381,7 +382,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 if (++ia == P.nA) { ia = 0; pa ^= 1; }
                 if (!res && ++ib == P.nB) { ib = 0; pb ^= 1; }
             }
-        } else if (P.amode == AMODE_RS) {
+        } else if (amode == AMODE_RS) {
             const uint32_t row16 = (uint32_t)swz >> 4;                        // one pixel row of the slab, in 16-byte units
             for (int ch = 0; ch < q.nchunk; ++ch) {
                 TM_MARK(2);
@@ -407,7 +408,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
             }
         } else {
             int step = 0;
-            const int ndc = (P.amode == AMODE_SLAB ? 3 : 1) * q.nchunk;
+            const int ndc = (amode == AMODE_SLAB ? 3 : 1) * q.nchunk;
             for (int dc = 0; dc < ndc; ++dc) {                                // SLAB: (dx, channel chunk); DXN: channel chunk
                 TM_MARK(2);
                 ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
@@ -476,7 +477,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 // and HALF of each weight sub-block, so the L2 -> SM weight traffic and the shared-memory operand reads per SM drop.
 // Used for the slab-staged layers whose weights stream (N = 128 / 256); the leader (cluster rank 0) issues the MMAs,
 // both CTAs run their own producer and epilogue groups on their own 128 rows.
-template <int NG, bool F16, bool MULTI, bool PAIR = false>
+template <int NG, bool F16, bool MULTI, bool PAIR = false, int AM = -1, int EP = -1>
 __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
@@ -489,6 +490,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and provably so for the compiler
     const int lane = threadIdx.x & 31;
+    const int amode = AM >= 0 ? AM : P.amode;               // AM / EP >= 0: staging mode / epilogue fixed at compile time
+#define EPI_OF(q_) (EP >= 0 ? EP : (q_).epi)
     // operand tiles need 1024-byte alignment for the 128-byte swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -539,16 +542,16 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             if (res) {                                                        // whole weight matrix once per CTA
                 const IgemmProblem& q = P.prob[0];
                 const int cin = q.nchunk * P.KC;
-                const int steps = (P.amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
+                const int steps = (amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
                 if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
                     for (int s = 0; s < steps; ++s) {
                         int kcoord = s * P.KC;                                // TAP / RS order: (tap, chunk)
-                        if (P.amode == AMODE_SLAB) {                          // SLAB order: (dx, chunk, dy)
+                        if (amode == AMODE_SLAB) {                          // SLAB order: (dx, chunk, dy)
                             const int dyi = s % 3, dc = s / 3;
                             const int dxi = dc / q.nchunk, ch = dc - dxi * q.nchunk;
                             kcoord = (dyi * 3 + dxi) * cin + ch * P.KC;
-                        } else if (P.amode == AMODE_DXN) {                    // DXN order: (chunk, dy); K' = (dy, Cin)
+                        } else if (amode == AMODE_DXN) {                    // DXN order: (chunk, dy); K' = (dy, Cin)
                             const int dyi = s % 3, ch = s / 3;
                             kcoord = dyi * cin + ch * P.KC;
                         }
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             for (it.init(P, blockIdx.x, gridDim.x); it.valid(); it.next()) {
                 const TileCoord tc = it.coord(P);
                 const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
-                if (P.amode == AMODE_TAP) {
+                if (amode == AMODE_TAP) {
                     const int steps = q.taps * q.nchunk;
                     for (int s = 0; s < steps; ++s) {
                         const int tap = s / q.nchunk;
@@ -596,8 +599,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 } else {
                     const int cin = q.nchunk * P.KC;
                     const uint32_t slab_bytes = (uint32_t)((P.TH * P.MT + 2) * P.TW * P.KC * 2);
-                    const bool dxn = P.amode == AMODE_DXN;
-                    const bool one_slab = P.amode != AMODE_SLAB;              // DXN / RS: a single slab per channel chunk
+                    const bool dxn = amode == AMODE_DXN;
+                    const bool one_slab = amode != AMODE_SLAB;              // DXN / RS: a single slab per channel chunk
                     for (int dxi = 0; dxi < (one_slab ? 1 : 3); ++dxi) {
                         for (int ch = 0; ch < q.nchunk; ++ch) {
                             ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
@@ -641,9 +644,9 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (!PAIR || pair_rank == 0) {                      // pair: only the leader issues MMAs
-            if (P.KC == 64)      mma_role<4, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else if (P.KC == 32) mma_role<2, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else                 mma_role<1, MULTI, PAIR>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            if (P.KC == 64)      mma_role<4, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else if (P.KC == 32) mma_role<2, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            else                 mma_role<1, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
         }
     } else {
         // =========================== epilogue (warps 2..9) ===========================
@@ -695,15 +698,15 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             const int n0 = (int)(blockIdx.x % q0.n_tiles) * P.n_out;
             float* sb0 = s_bias + (grp * 2) * (512 / NG);
             for (int i = etid; i < P.n_out; i += 128)
-                sb0[i] = __ldg(q0.bias + (q0.epi == EPI_CONVT ? (n0 + i) % q0.convt_cout
-                                          : q0.epi == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
+                sb0[i] = __ldg(q0.bias + (EPI_OF(q0) == EPI_CONVT ? (n0 + i) % q0.convt_cout
+                                          : EPI_OF(q0) == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
         }
         // The barrier at the top of a tile publishes the tile's bias and the "staging tile is free again" news.  With a
         // static bias it can go when nothing is staged (OUTCONV), or when tiles are single-chunk STOREs alternating
         // between two staging tiles: there thread 0 waits for the PREVIOUS tile's store to have read its tile right
         // before the mid-tile barrier every thread passes anyway (that store was issued a whole tile ago).
-        const int epi0 = P.prob[0].epi;
-        const int chunks_per_tile = P.amode == AMODE_DXN ? 1 : P.MT * P.BN / P.CB;
+        const int epi0 = EPI_OF(P.prob[0]);
+        const int chunks_per_tile = amode == AMODE_DXN ? 1 : P.MT * P.BN / P.CB;
         const bool early_wait = bias_static && !P.cbatch && P.cslots == 2 && chunks_per_tile == 1 && epi0 == EPI_STORE && P.lean_sync != 0;
         const bool skip_top_bar = bias_static && P.lean_sync != 0 && (epi0 == EPI_OUTCONV || early_wait);
         asm volatile("griddepcontrol.wait;" ::: "memory");          // before the first store / activation read of this role
@@ -727,9 +730,9 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         for (it.init(P, blockIdx.x + grp * gridDim.x, NG * gridDim.x); it.valid(); it.next()) {
             const TileCoord tc = it.coord(P);
             const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
-            const int xoff = P.amode == AMODE_RS ? 1 : 0;           // RS: output column j sits at slab column j + 1
+            const int xoff = amode == AMODE_RS ? 1 : 0;           // RS: output column j sits at slab column j + 1
             const int y = tc.y0 + ty, x = tc.x0 + xoff + tx;
-            const bool colok = P.amode != AMODE_RS || tx < P.VW;    // RS: the last two columns of a row are wrap-around garbage
+            const bool colok = amode != AMODE_RS || tx < P.VW;    // RS: the last two columns of a row are wrap-around garbage
             const bool valid = (y < q.H) && (x < q.W) && colok;
             const int srow = ty * P.VW + tx;                        // row inside the (CB, VW, TH) store box
             // bias of this tile, double-buffered by iteration parity (a slow thread may still read the previous one)
@@ -738,8 +741,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             if (!bias_static) {
                 const float* bsrc = q.bias + (q.bias_img_stride ? (size_t)tc.b * q.bias_img_stride : 0);
                 for (int i = etid; i < P.n_out; i += 128)
-                    sb[i] = __ldg(bsrc + (q.epi == EPI_CONVT ? (tc.n0 + i) % q.convt_cout
-                                          : q.epi == EPI_CONVTFIX ? ((tc.n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q.convt_cout : tc.n0 + i));
+                    sb[i] = __ldg(bsrc + (EPI_OF(q) == EPI_CONVT ? (tc.n0 + i) % q.convt_cout
+                                          : EPI_OF(q) == EPI_CONVTFIX ? ((tc.n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q.convt_cout : tc.n0 + i));
             }
             TM_MARK(0);                                         // 0: tile bookkeeping
             if (etid == 0 && !skip_top_bar) WAIT_STORE_READS(); // the store that last used the next staging tile has left smem
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             const uint32_t taddr0 = tmem_base + (uint32_t)(acc * P.BN * P.MT) + ((uint32_t)(quarter * 32) << 16);
             uint32_t taddr = taddr0;
 
-            if (P.amode == AMODE_DXN) {
+            if (amode == AMODE_DXN) {
                 // ---- combine the three dx column groups: out[p] = E0[p-1] + E1[p] + E2[p+1]  (p = lane = slab column)
                 const int N = P.n_out;
                 const bool inner = lane >= 1 && lane <= P.VW;                    // the 30 valid output columns
@@ -778,7 +781,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                             f[i] = fmaxf((l + __uint_as_float(e1[i])) + (r + bb[u]), 0.f);   // every DXN layer ends in ReLU
                         }
                     }
-                    if (q.epi == EPI_STORE) {
+                    if (EPI_OF(q) == EPI_STORE) {
                         if (inner) {
 #pragma unroll
                             for (int v = 0; v < 2; ++v) {
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
-                if (q.epi == EPI_STORE) {
+                if (EPI_OF(q) == EPI_STORE) {
                     if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 } else if (inner && valid) {
                     q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 }
-            } else if (q.epi == EPI_STORE || q.epi == EPI_CONVT) {
+            } else if (EPI_OF(q) == EPI_STORE || EPI_OF(q) == EPI_CONVT) {
               // One staging tile per CB-channel chunk.  cbatch: the tile's chunks all have their own staging tile, so the
               // whole accumulator is converted first and fence / barrier / TMA stores happen ONCE per tile; otherwise the
               // chunks rotate through `cslots` tiles with a barrier pair per chunk.
@@ -833,7 +836,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                   const int n = tc.n0 + c0, yb = tc.y0 + mb * P.TH;
                   const void* tm;
                   int cch;
-                  if (q.epi == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
+                  if (EPI_OF(q) == EPI_STORE) { tm = &P.tmC[tc.pi]; cch = n; }
                   else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                ::"l"((uint64_t)tm), "r"(c_tile), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
@@ -925,7 +928,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
               }
-            } else if (q.epi == EPI_CONVTFIX) {
+            } else if (EPI_OF(q) == EPI_CONVTFIX) {
                 // n tile = (phase t along the free axis, channel block); columns [up | mid0 | mid1], CC channels each
                 const int CC = P.BN / 3;
                 const int nt = tc.n0 / P.BN, nsub = q.convt_cout / CC;
@@ -1005,7 +1008,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(empty_bar); else ptx::mbar_arrive(empty_bar); }
-                if (q.epi == EPI_OUTCONV) {
+                if (EPI_OF(q) == EPI_OUTCONV) {
                     if (valid) q.aux[((size_t)tc.b * q.H + y) * q.W + x] = dot + q.scalar;
                 } else {
                     const float a = 1.f / (1.f + expf(-(dot + q.scalar)));
@@ -1046,6 +1049,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         }
         TM_FLUSH(8 + 8 * (grp & 1), lane == 0 && quarter == 0);
 #undef EPI_BAR
+#undef EPI_OF
 #undef NEXT_CSLOT
 #undef WAIT_STORE_READS
         if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores landed
