@@ -126,6 +126,7 @@ struct Engine {
     int opt_fusefix = 1;
     int opt_fixcc = 0;
     int opt_convt_batch = 1;
+    int opt_tb = 1;           // per-tap staged tiles may span two frames
     int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
     int opt_pair = 3;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
@@ -598,21 +599,24 @@ static View sub_view(const View& v, int choff, int C) {
 // Instantiations of igemm_tc_kernel.  The generic ones (AM = EP = -1) branch on the staging mode and epilogue at run time
 // and serve every plan; the bf16 hot path additionally gets instantiations with both fixed at compile time -- a third of
 // the code size each, so the single-warp roles miss the instruction cache less and skip the uniform mode branches.
-struct IgemmKernelKey { int ng, f16, multi, pair, am, ep; };
 #define AAU_IGEMM_GENERIC(X) \
-    X(2, false, false, false, -1, -1) X(2, true, false, false, -1, -1) X(4, false, false, false, -1, -1) X(4, true, false, false, -1, -1) \
-    X(2, false, true, false, -1, -1) X(2, true, true, false, -1, -1) X(2, false, false, true, -1, -1) X(2, true, false, true, -1, -1) \
-    X(2, false, true, true, -1, -1) X(2, true, true, true, -1, -1)
+    X(2, false, false, false, -1, -1, -1, -1) X(2, true, false, false, -1, -1, -1, -1) X(4, false, false, false, -1, -1, -1, -1) X(4, true, false, false, -1, -1, -1, -1) \
+    X(2, false, true, false, -1, -1, -1, -1) X(2, true, true, false, -1, -1, -1, -1) X(2, false, false, true, -1, -1, -1, -1) X(2, true, false, true, -1, -1, -1, -1) \
+    X(2, false, true, true, -1, -1, -1, -1) X(2, true, true, true, -1, -1, -1, -1)
+// (NG, fp16, multi-problem, CTA pair, staging mode, epilogue, MMAs per sub-block = KC / 16, fused MaxPool)
 #define AAU_IGEMM_SPECIALISED(X) \
-    X(2, false, false, false, AMODE_RS, EPI_STORE) X(4, false, false, false, AMODE_RS, EPI_STORE) X(2, false, false, false, AMODE_RS, EPI_OUTCONV) \
-    X(2, false, false, false, AMODE_DXN, EPI_STORE) X(2, false, false, true, AMODE_SLAB, EPI_STORE) \
-    X(2, false, false, false, AMODE_TAP, EPI_GATE) X(2, false, false, false, AMODE_TAP, EPI_CONVT) X(4, false, false, false, AMODE_TAP, EPI_CONVT) \
-    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX) X(2, false, false, true, AMODE_TAP, EPI_STORE) X(2, false, true, true, AMODE_TAP, EPI_STORE)
-static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep) {
-#define X(NG, F16, MULTI, PAIR, AM, EP) \
-    if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP)) return (const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP>;
+    X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, false, AMODE_RS, EPI_STORE, 4, 0) \
+    X(2, false, false, false, AMODE_RS, EPI_OUTCONV, 2, 0) \
+    X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, false, AMODE_DXN, EPI_STORE, 2, 0) \
+    X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 1) \
+    X(2, false, false, false, AMODE_TAP, EPI_GATE, 4, 0) X(2, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) \
+    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0)
+static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep, int kk, int pl) {
+#define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) \
+    if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP) && kk == (KK) && pl == (PL)) \
+        return (const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP, KK, PL>;
     AAU_IGEMM_SPECIALISED(X)
-    if (am != -1 || ep != -1) return igemm_kernel(ng, f16, multi, pair, -1, -1);
+    if (am != -1 || ep != -1 || kk != -1 || pl != -1) return igemm_kernel(ng, f16, multi, pair, -1, -1, -1, -1);
     AAU_IGEMM_GENERIC(X)
 #undef X
     return nullptr;
@@ -695,19 +699,27 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         if (slab && th < 4) continue;
         if (want_pool && th < 2) continue;
         const int mt = (mt_want == 2 && H > th && e.opt_mt_shape != 0) ? 2 : 1;   // rows of a tile: th * mt
-        double cost = (double)((H + th * mt - 1) / (th * mt) * (th * mt)) * ((W + tw - 1) / tw * tw);
-        if (slab) cost *= 1.0 + 0.5 * 2.0 / (th * mt);     // halo rows cost bandwidth, not MMA time
-        if (cost < best) { best = cost; P.TW = tw; P.TH = th; }
+        // small images under per-tap staging: a tile may span two frames (TMA boxes over the batch dimension), which
+        // halves the row padding -- 35 x 46 bridge: 8x16 tiles pad to 40 x 48, 4x16 x 2 frames to 36 x 48
+        const bool tb_ok = e.opt_tb != 0 && !slab && !dxn && !rs && !cfix && !want_pool && (d0.epi == EPI_STORE || d0.epi == EPI_CONVT) &&
+                           d0.in.B % 2 == 0 && th >= 2 && d0.bias_img == nullptr;   // (a per-image bias is staged per tile)
+        for (int tb = 1; tb <= (tb_ok ? 2 : 1); ++tb) {
+            const int rows = th / tb * mt;
+            double cost = (double)((H + rows - 1) / rows * rows) * ((W + tw - 1) / tw * tw);
+            if (slab) cost *= 1.0 + 0.5 * 2.0 / rows;      // halo rows cost bandwidth, not MMA time
+            if (tb == 2) cost *= 1.03;                     // only where it saves padding for real
+            if (cost < best) { best = cost; P.TW = tw; P.TH = th / tb; P.TB = tb; }
+        }
     }
     P.VW = P.TW;
-    if (dxn || rs) { P.TW = 32; P.TH = 4; P.VW = 30; }
+    if (dxn || rs) { P.TW = 32; P.TH = 4; P.VW = 30; P.TB = 1; }
     P.MT = (mt_want == 2 && H > P.TH) ? 2 : 1;
     P.tw_shift = ilog2(P.TW);
     const int swz = P.KC * 2;
     const int nchunk = Cin / P.KC;
     const int steps = (dxn ? 3 : d0.w->taps) * nchunk;            // k-steps (one B sub-block each) per tile
     // CTA pairs (cta_group::2): slab-staged layers whose weights stream, one N tile, an even number of tiles
-    const int tiles_total0 = d0.in.B * ((W + P.VW - 1) / P.VW) * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
+    const int tiles_total0 = d0.in.B / P.TB * ((W + P.VW - 1) / P.VW) * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
     const bool pair_slab = (e.opt_pair & 1) != 0 && slab && !dxn && !rs && descs.size() == 1 && (size_t)9 * Cin * BN * 2 > 112 * 1024;
     // ... and per-tap staged STORE layers with streamed weights (the dilated ASPP branches as one three-problem launch,
     // the ASPP projection): every problem has an even number of tiles, so the two CTAs of a pair stay on one problem
@@ -801,7 +813,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         // activations: (C, W, H, B)
         const uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)d.in.W, (uint64_t)d.in.H, (uint64_t)d.in.B};
         const uint64_t astr[3] = {(uint64_t)d.in.ld * 2, (uint64_t)d.in.W * d.in.ld * 2, (uint64_t)d.in.H * d.in.W * d.in.ld * 2};
-        const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH * P.MT + 2 : P.TH), 1u};
+        const uint32_t abox[4] = {(uint32_t)P.KC, (uint32_t)P.TW, (uint32_t)(slab ? P.TH * P.MT + 2 : P.TH), (uint32_t)P.TB};
         if (!encode_map(e, &q.tmA, d.in.p + (size_t)d.in.choff * 2, 4, adims, astr, abox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
         const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
@@ -818,7 +830,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
         q.H = H; q.W = W;
         q.tiles_x = (W + P.VW - 1) / P.VW;
         q.tiles_per_img = q.tiles_x * ((H + P.TH * P.MT - 1) / (P.TH * P.MT));
-        q.m_tiles = d.in.B * q.tiles_per_img;
+        q.m_tiles = d.in.B / P.TB * q.tiles_per_img;
         q.n_tiles = Ntot / n_out;
         q.tile_begin = tile_begin;
         q.fd_n_tiles = make_fastdiv((uint32_t)q.n_tiles);
@@ -836,7 +848,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     }
     P.total_tiles = tile_begin;
     if (tma_out) {
-        const uint32_t cbox[4] = {(uint32_t)P.CB, (uint32_t)P.VW, (uint32_t)P.TH, 1u};
+        const uint32_t cbox[4] = {(uint32_t)P.CB, (uint32_t)P.VW, (uint32_t)P.TH, (uint32_t)P.TB};
         if (d0.epi == EPI_STORE || d0.epi == EPI_GATE) {
             for (int i = 0; i < P.nprob; ++i) {
                 const View& o = descs[i].out;                     // GATE: the skip view that is scaled in place
@@ -892,13 +904,14 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     if (P.b_resident && Ntot != n_out) grid = std::max(Ntot / n_out, grid / (Ntot / n_out) * (Ntot / n_out));   // multiple of n_tiles
     if (pair) grid &= ~1;                                          // clusters of two
     oi.name += " [" + std::string(cfix ? "tap2+fix" : (rs ? "rs" : (dxn ? "dxn" : (slab ? "slab" : "tap")))) + (P.b_resident ? ",Bres" : "") + (P.pool ? ",pool" : "") + " BN" + std::to_string(BN) + " KC" + std::to_string(P.KC) +
-               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + (pair ? " pair" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
+               " " + std::to_string(P.TH) + "x" + std::to_string(P.TW) +  (P.MT == 2 ? " MT2" : "") + (P.TB == 2 ? " x2fr" : "") + (P.cslots >= 2 ? " c" + std::to_string(P.cslots) + (P.cbatch ? "b" : "") : "") + (ng == 4 ? " g4" : "") + (pair ? " pair" : "") + " nA" + std::to_string(P.nA) + " nB" + std::to_string(P.nB) + " x" +
                std::to_string(ctas) + "]";
     plan.info.back().name = oi.name;
     const bool f16k = e.is_fp16();
     // programmatic dependent launch when the op before this one in the stream is a kernel (not the side-stream join)
     const bool pdl = e.opt_pdl != 0 && plan.info.size() >= 2 && plan.info[plan.info.size() - 2].kernel[0] != '(';
-    const void* fn = igemm_kernel(ng, f16k, P.nprob > 1, pair, e.opt_spec != 0 ? P.amode : -1, e.opt_spec != 0 ? d0.epi : -1);
+    const bool spec = e.opt_spec != 0;
+    const void* fn = igemm_kernel(ng, f16k, P.nprob > 1, pair, spec ? P.amode : -1, spec ? d0.epi : -1, spec ? P.KC / 16 : -1, spec ? P.pool : -1);
     if (!fn) return e.fail(AAU_ERR_INVALID, "no igemm_tc_kernel instantiation for this plan");
     plan.ops.push_back([P, grid, smem, patch_aux, ng, pdl, pair, fn](const FwdArgs& a) -> cudaError_t {
         IgemmParams Q = P;
@@ -1282,7 +1295,7 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     };
     bool raised = raise_smem((const void*)stem_tc_kernel<false>) && raise_smem((const void*)stem_tc_kernel<true>);
-#define X(NG, F16, MULTI, PAIR, AM, EP) raised = raised && raise_smem((const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP>);
+#define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) raised = raised && raise_smem((const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP, KK, PL>);
     AAU_IGEMM_GENERIC(X)
     AAU_IGEMM_SPECIALISED(X)
 #undef X
@@ -1596,7 +1609,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
     const std::pair<const char*, int*> plan_options[] = {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
-        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
+        {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"tb", &e.opt_tb}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
         {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
     for (const auto& o : plan_options) {
         if (n == o.first) {

@@ -147,6 +147,7 @@ struct alignas(64) IgemmParams {
     int lean_sync;          // 1: drop the per-tile top barrier where a static bias and alternating staging tiles allow it
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int pair_order;         // CTA pairs over several N tiles: consecutive tiles are two M tiles of one N tile
+    int TB;                 // images per tile (per-tap staging of small images: the TMA boxes span TB frames of TH rows each)
     int* err;
 };
 
@@ -212,8 +213,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
         mt = 2 * j + (local & 1);
     }
     tc.pi = pi;
-    tc.b = (int)fdiv((uint32_t)mt, q.fd_tiles_per_img);
-    const int r = mt - tc.b * q.tiles_per_img;
+    const int bt = (int)fdiv((uint32_t)mt, q.fd_tiles_per_img);
+    tc.b = bt * P.TB;
+    const int r = mt - bt * q.tiles_per_img;
     const int tyi = (int)fdiv((uint32_t)r, q.fd_tiles_x);
     tc.y0 = tyi * P.TH * P.MT;
     tc.x0 = (r - tyi * q.tiles_x) * P.VW - (P.amode >= AMODE_DXN ? 1 : 0);   // DXN / RS: slab column 0 is the left halo
@@ -271,7 +273,7 @@ struct TileIter {
         if (!incremental) return decode_tile(P, t);
         TileCoord tc;
         tc.pi = 0;
-        tc.b = b;
+        tc.b = b * P.TB;
         tc.y0 = y * P.TH * P.MT;
         tc.x0 = x * P.VW - (P.amode >= AMODE_DXN ? 1 : 0);
         tc.n0 = nt * P.n_out;
@@ -477,7 +479,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
 // and HALF of each weight sub-block, so the L2 -> SM weight traffic and the shared-memory operand reads per SM drop.
 // Used for the slab-staged layers whose weights stream (N = 128 / 256); the leader (cluster rank 0) issues the MMAs,
 // both CTAs run their own producer and epilogue groups on their own 128 rows.
-template <int NG, bool F16, bool MULTI, bool PAIR = false, int AM = -1, int EP = -1>
+template <int NG, bool F16, bool MULTI, bool PAIR = false, int AM = -1, int EP = -1, int KKT = -1, int PL = -1>
 __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_kernel(const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[IGEMM_MAX_SLOTS], empty_a[IGEMM_MAX_SLOTS];
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     const int lane = threadIdx.x & 31;
     const int amode = AM >= 0 ? AM : P.amode;               // AM / EP >= 0: staging mode / epilogue fixed at compile time
 #define EPI_OF(q_) (EP >= 0 ? EP : (q_).epi)
+    const bool fused_pool = PL >= 0 ? (PL != 0) : (P.pool != 0);   // KKT / PL >= 0: MMAs per sub-block / fused MaxPool fixed at compile time
     // operand tiles need 1024-byte alignment for the 128-byte swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -644,9 +647,13 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (!PAIR || pair_rank == 0) {                      // pair: only the leader issues MMAs
-            if (P.KC == 64)      mma_role<4, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else if (P.KC == 32) mma_role<2, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-            else                 mma_role<1, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            if constexpr (KKT > 0) {
+                mma_role<KKT, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            } else {
+                if (P.KC == 64)      mma_role<4, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+                else if (P.KC == 32) mma_role<2, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+                else                 mma_role<1, MULTI, PAIR, AM>(P, smem_a, smem_b, full_a, empty_a, full_b, empty_b, &b_res_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+            }
         }
     } else {
         // =========================== epilogue (warps 2..9) ===========================
@@ -810,7 +817,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (early_wait && etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     EPI_BAR();
-                    if (P.pool) {
+                    if (fused_pool) {
                         pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     if (etid == 0) {
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                      ::"l"((uint64_t)&P.tmC[0]), "r"(cs), "r"(tc.n0), "r"(tc.x0 + 1), "r"(tc.y0), "r"(tc.b) : "memory");
-                        if (P.pool)
+                        if (fused_pool)
                             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                          ::"l"((uint64_t)&P.tmP), "r"(ps), "r"(tc.n0), "r"((tc.x0 + 1) >> 1), "r"(tc.y0 >> 1), "r"(tc.b) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -840,7 +847,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                   else { const int ab = n / q.convt_cout; tm = &P.tmC[ab]; cch = n - ab * q.convt_cout; }
                   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                ::"l"((uint64_t)tm), "r"(c_tile), "r"(cch), "r"(tc.x0 + xoff), "r"(yb), "r"(tc.b) : "memory");
-                  if (P.pool)
+                  if (fused_pool)
                       asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                    ::"l"((uint64_t)&P.tmP), "r"(p_tile), "r"(n), "r"((tc.x0 + xoff) >> 1), "r"(yb >> 1), "r"(tc.b) : "memory");
               };
@@ -896,7 +903,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         EPI_BAR();
                         TM_MARK(5);                                             // 5: proxy fence + barrier
-                        if (P.pool) {
+                        if (fused_pool) {
                             pool_staged_tile(cs, ps, P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             EPI_BAR();
@@ -914,7 +921,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
               if (batch) {                                                      // cslot is back at 0: chunk j sits in staging tile j
                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                   EPI_BAR();
-                  if (P.pool) {
+                  if (fused_pool) {
                       for (int j = 0; j < P.cslots; ++j)
                           pool_staged_tile(c_grp + (uint32_t)(j * P.c_slot_bytes), p_grp + (uint32_t)(j * P.p_slot_bytes), P.TH, P.VW, c_pitch, swz_mask, etid, f16);
                       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

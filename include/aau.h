@@ -147,10 +147,18 @@ int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel
 /* Copy one named intermediate of the LAST forward (NHWC, activation dtype) to `dst` (device, element count
  * returned through numel/C); names: x1 x2 x3 x4 p4 bridge d4 d3 d2 (used by layer-by-layer parity tests). */
 int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff);
-/* Options: "amode" forces the A-operand staging mode of the 3x3 convolutions (-1 auto, 0 per-tap boxes, 1 halo
- * slabs); "resident" (1/0) allows / forbids keeping a layer's whole weight matrix in shared memory; "ctas" (0 auto,
- * 1..3) caps the CTAs per SM of the GEMM kernel; "profile" (0/1) records CUDA events around every launch of the
- * following forwards (aau_op_profile). */
+/* Planner options (test / measurement aids; every combination computes the same function, parity tests force them all):
+ *   "amode"    A-operand staging of the 3x3 convolutions: -1 auto, 0 per-tap boxes, 1 halo slabs, 2 dx-stacked, 3 row-shifted
+ *   "rs" "rs_mt" "mt" "mt_shape" "slab_max_bn" "dxn_full"   individual staging choices (row-shifted taps, stacked M-blocks,
+ *              tile-shape search, un-split dx-stacked weights)
+ *   "resident" 1/0 allow / forbid keeping a layer's whole weight matrix in shared memory
+ *   "ctas" (0 auto, 1..2 CTAs per SM), "ng" (0 auto, 2 / 4 epilogue groups = TMEM stages), "cslots", "convt_batch", "lean"
+ *   "pair"     CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers (default 3)
+ *   "spec"     1/0 use the kernel instantiations specialised per (staging mode, epilogue, K step, fused pool)
+ *   "stem_tc"  1/0 uint8 frames run d1.0 on the tensor cores (0: packed-fp32 stem, as float frames always do)
+ *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
+ *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
+ *   "profile"  0/1 record CUDA events around every launch of the following forwards (aau_op_profile). */
 int aau_set_option(aau_handle* h, const char* name, int value);
 
 #ifdef __cplusplus

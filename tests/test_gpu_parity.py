@@ -284,6 +284,8 @@ OPTION_SETS = [
     {"titer": 0, "pdl": 0, "side": 0, "fusepool": 0},
     {"pair": 0, "lean": 0, "convt_batch": 0},   # no CTA pairs (cta_group::2), per-tile top barrier everywhere, per-chunk transposed-conv sync
     {"dxn_full": 0},                # u2.conv.0 with its dx-stacked weights split in two N tiles
+    {"spec": 0, "tb": 0},           # generic kernel instantiations only, one frame per tile
+    {"pair": 1, "stem_tc": 0},      # CTA pairs for slab-staged layers only
 ]
 
 
