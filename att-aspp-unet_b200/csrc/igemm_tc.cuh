@@ -283,14 +283,18 @@ struct TileIter {
 
 // MaxPool2d(2) of a staged output tile (rows = th x vw pixels, c_pitch bytes each, TMA-swizzled) into a staged
 // pooled tile ((th/2) x (vw/2) pixels, same pitch / swizzle).  One 16-byte vector (8 channels) per thread-iteration;
-// c_pitch / 16 is a power of two, so a thread keeps its vector index and walks pooled pixels (no divisions).
+// c_pitch / 16 is a power of two, so a thread keeps its vector index and walks pooled pixels.
 __device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int th, int vw, int c_pitch, uint32_t swz_mask,
                                                  int etid, int f16) {
     const int PW = vw >> 1, PH = th >> 1;
     const int lcv = 31 - __clz(c_pitch >> 4);                     // log2(vectors per pixel): 1, 2 or 3
-    const int v = etid & ((1 << lcv) - 1), px0 = etid >> lcv, pstep = 128 >> lcv;   // 128 threads per epilogue group
-    for (int py = 0; py < PH; ++py)
-        for (int px = px0; px < PW; px += pstep) {
+    const int v = etid & ((1 << lcv) - 1), i0 = etid >> lcv, istep = 128 >> lcv;    // 128 threads per epilogue group
+    // pooled pixels are dealt out in one flat sequence (i = py * PW + px), so a 2 x 15 pooled tile occupies 30 of the 32
+    // thread slots once instead of 15 slots twice; i / PW by multiply-shift (exact for i * PW < 2^16)
+    const uint32_t inv_pw = (65536u + (uint32_t)PW - 1u) / (uint32_t)PW;
+    for (int i = i0; i < PH * PW; i += istep) {
+        {
+            const int py = (int)(((uint32_t)i * inv_pw) >> 16), px = i - py * PW;
             const int r00 = (2 * py) * vw + 2 * px;
             uint32_t o0 = (uint32_t)(r00 * c_pitch + v * 16), o1 = o0 + (uint32_t)c_pitch;
             uint32_t o2 = o0 + (uint32_t)(vw * c_pitch), o3 = o2 + (uint32_t)c_pitch;
@@ -301,6 +305,7 @@ __device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int t
             po ^= ((po >> 7) & swz_mask) << 4;
             sts128(ps + po, m);
         }
+    }
 }
 
 __device__ __forceinline__ void tap_offsets(const IgemmProblem& q, int tap, int& dy, int& dx) {
@@ -877,12 +882,20 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                             if (colok) sts128(cs_row + ((uint32_t)(col * 2) ^ xr), o);
                         };
                         if ((P.CB & 31) == 0) {
+                            // 16 accumulator columns at a time, the next 16 in flight while these are converted (one x32
+                            // load per 32 columns left the whole TMEM read latency in front of the first FADD: 21 % of
+                            // d1.1's epilogue samples)
+                            uint32_t ra[32], rb[32];
+                            ptx::tmem_ld_32x16(taddr + c0, ra);
                             for (int cc = 0; cc < P.CB; cc += 32) {
-                                uint32_t r[32];
-                                ptx::tmem_ld_32x32(taddr + c0 + cc, r);
                                 ptx::tmem_ld_wait();
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) convert8(r + v * 8, cc + v * 8);
+                                ptx::tmem_ld_32x16(taddr + c0 + cc + 16, rb);
+                                convert8(ra, cc);
+                                convert8(ra + 8, cc + 8);
+                                ptx::tmem_ld_wait();
+                                if (cc + 32 < P.CB) ptx::tmem_ld_32x16(taddr + c0 + cc + 32, ra);
+                                convert8(rb, cc + 16);
+                                convert8(rb + 8, cc + 24);
                             }
                         } else {                                                     // CB == 16
                             uint32_t r[32];
