@@ -128,7 +128,7 @@ struct Engine {
     int opt_convt_batch = 1;
     int opt_tb = 1;           // per-tap staged tiles may span two frames
     int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
-    int opt_pair = 3;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers
+    int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N layers
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
@@ -602,7 +602,7 @@ static View sub_view(const View& v, int choff, int C) {
 #define AAU_IGEMM_GENERIC(X) \
     X(2, false, false, false, -1, -1, -1, -1) X(2, true, false, false, -1, -1, -1, -1) X(4, false, false, false, -1, -1, -1, -1) X(4, true, false, false, -1, -1, -1, -1) \
     X(2, false, true, false, -1, -1, -1, -1) X(2, true, true, false, -1, -1, -1, -1) X(2, false, false, true, -1, -1, -1, -1) X(2, true, false, true, -1, -1, -1, -1) \
-    X(2, false, true, true, -1, -1, -1, -1) X(2, true, true, true, -1, -1, -1, -1)
+    X(2, false, true, true, -1, -1, -1, -1) X(2, true, true, true, -1, -1, -1, -1) X(4, false, false, true, -1, -1, -1, -1) X(4, true, false, true, -1, -1, -1, -1)
 // (NG, fp16, multi-problem, CTA pair, staging mode, epilogue, MMAs per sub-block = KC / 16, fused MaxPool)
 #define AAU_IGEMM_SPECIALISED(X) \
     X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, false, AMODE_RS, EPI_STORE, 4, 0) \
@@ -610,7 +610,10 @@ static View sub_view(const View& v, int choff, int C) {
     X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, false, AMODE_DXN, EPI_STORE, 2, 0) \
     X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 1) \
     X(2, false, false, false, AMODE_TAP, EPI_GATE, 4, 0) X(2, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) \
-    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0)
+    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0) \
+    X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 0) \
+    X(2, false, false, true, AMODE_RS, EPI_OUTCONV, 2, 0) \
+    X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, true, AMODE_DXN, EPI_STORE, 2, 0)
 static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep, int kk, int pl) {
 #define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) \
     if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP) && kk == (KK) && pl == (PL)) \
@@ -724,7 +727,13 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // ... and per-tap staged STORE layers with streamed weights (the dilated ASPP branches as one three-problem launch,
     // the ASPP projection): every problem has an even number of tiles, so the two CTAs of a pair stay on one problem
     const bool pair_tap = (e.opt_pair & 2) != 0 && !slab && !cfix && (descs.size() > 1 || (size_t)d0.w->taps * Cin * BN * 2 > 112 * 1024);
-    const bool pair = (pair_slab || pair_tap) && d0.epi == EPI_STORE && (Ntot == BN || pair_tap) && BN >= 128 && tiles_total0 % 2 == 0 && tiles_total0 >= 2;
+    // ... and the small-N layers whose weights are resident (row-shifted / dx-stacked staging): each CTA keeps half of
+    // the weight rows, so the B operand read per MMA and SM halves (32 + N/8 instead of 32 + N/4 cycles), and one MMA
+    // issuer drives two SMs, which halves the per-tile issue latency that paces these layers
+    const bool pair_res = (e.opt_pair & 4) != 0 && (rs || dxn) && descs.size() == 1 && e.opt_resident != 0 && Ntot == n_out &&
+                          (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && tiles_total0 % 2 == 0 && tiles_total0 >= 2 &&
+                          (size_t)steps * (BN / 2) * swz <= res_limit;
+    const bool pair = pair_res || ((pair_slab || pair_tap) && d0.epi == EPI_STORE && (Ntot == BN || pair_tap) && BN >= 128 && tiles_total0 % 2 == 0 && tiles_total0 >= 2);
     P.pair_order = (pair && Ntot != BN) ? 1 : 0;                  // several N tiles: a pair walks two M tiles of one N tile
     P.b_slot_bytes = (pair ? BN / 2 : BN) * swz;
     P.a_slot_bytes = slab ? (((P.TH * P.MT + 2) * P.TW * swz + 1023) & ~1023) : 128 * swz;
@@ -742,13 +751,13 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // CTA fits and four accumulators fit in the 512 TMEM columns, that CTA runs 4 stages / groups instead.
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
     // n_tiles so that the static striding keeps every CTA on the same N tile
-    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0 && !pair;
+    const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0 && (!pair || pair_res);
     const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
     auto cols_for = [&](int stages) { int c = 32; while (c < stages * BN * P.MT) c <<= 1; return c; };
-    int ctas = (BN <= 128 && !pair) ? 2 : 1;                      // measured: 2 CTAs co-reside, a third only queues
+    int ctas = (BN <= 128 && (!pair || pair_res)) ? 2 : 1;                      // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / cols_for(2));
     if (e.opt_ctas != 0) ctas = std::min(std::abs(e.opt_ctas), 512 / cols_for(2));
-    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE && descs.size() == 1 && !pair;
+    const bool ng4_ok = 4 * BN * P.MT <= 512 && e.opt_ng != 2 && d0.epi != EPI_GATE && descs.size() == 1 && (!pair || pair_res);
     // transposed convs with four (a,b) chunks per tile: one CTA with four groups, each staging all four chunks behind a
     // single fence / barrier / store group, beats two CTAs that sync per chunk (A/B on u1.up: -8 %)
     if (d0.epi == EPI_CONVT && ng4_ok && P.MT * BN / P.CB == 4 && e.opt_ctas == 0 && e.opt_cslots == 0 && e.opt_convt_batch != 0) ctas = 1;
@@ -767,6 +776,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
                 const bool res = pass < 3 && can_res && steps <= 64 && (size_t)res_bytes <= res_limit;
                 if (pass < 3 && !res) continue;
                 if (rs && !res) continue;                          // row-shifted taps index the resident weight matrix
+                if (pair_res && !res) continue;                    // this pair flavour keeps the weights resident
                 const int sel = pass % 3;
                 const bool cbatch = sel == 0;
                 if (cfix && (!cbatch || !res)) continue;           // both phases of a chunk are staged side by side; weights resident

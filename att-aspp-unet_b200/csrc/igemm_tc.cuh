@@ -403,10 +403,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                         const uint32_t shift = (uint32_t)((tap / 3) * P.TW + (tap % 3)) * row16;
                         const uint32_t b_lo = b_base + (uint32_t)(tap * q.nchunk + ch) * b_slot16;
                         if (P.MT == 2)                                        // second M-block: TH rows further down the slab
-                            mma_subblock<KK>(d_tmem + P.BN, a_lo + shift + a_mb16, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
-                        mma_subblock<KK>(d_tmem, a_lo + shift, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
+                            mma_subblock<KK, PAIR>(d_tmem + P.BN, a_lo + shift + a_mb16, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
+                        mma_subblock<KK, PAIR>(d_tmem, a_lo + shift, b_lo, desc_hi, idesc, tap == 0 ? accumulate : 1u);
                     }
-                    ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
+                    if (PAIR) ptx::umma_commit_pair(empty_a + 8u * (uint32_t)ia); else ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
                 }
                 __syncwarp();
                 TM_MARK(3);
@@ -421,7 +421,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 TM_MARK(1);
                 const uint32_t a_lo = a_base + ia * a_slot16;
-                if (res && !PAIR) {
+                if (res) {
                     // resident weights: nothing to wait for between the vertical taps, so all of them go out under one
                     // election (a fence + elect + warp sync per four MMAs kept the issue rate of the one-CTA-per-SM
                     // dx-stacked layer at 87 cycles per MMA against the 56-cycle operand-read floor)
@@ -431,10 +431,10 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                         for (int dyi = 0; dyi < 3; ++dyi) {
                             const uint32_t b_lo = b_base + (uint32_t)(step + dyi) * b_slot16;
                             if (P.MT == 2)
-                                mma_subblock<KK>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
-                            mma_subblock<KK>(d_tmem, a_lo + dyi * a_dy16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
+                                mma_subblock<KK, PAIR>(d_tmem + P.BN, a_lo + dyi * a_dy16 + a_mb16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
+                            mma_subblock<KK, PAIR>(d_tmem, a_lo + dyi * a_dy16, b_lo, desc_hi, idesc, dyi == 0 ? accumulate : 1u);
                         }
-                        ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
+                        if (PAIR) ptx::umma_commit_pair(empty_a + 8u * (uint32_t)ia); else ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
                     }
                     __syncwarp();
                     step += 3;
@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 const int cin = q.nchunk * P.KC;
                 const int steps = (amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
                 if (ptx::elect_one()) {
-                    ptx::mbar_expect_tx(&b_res_bar, (uint32_t)(steps * P.b_slot_bytes));
+                    // pair: each CTA keeps HALF of the weight rows of every sub-block; both halves complete the leader's barrier
+                    if (!PAIR || pair_rank == 0) ptx::mbar_expect_tx(&b_res_bar, (uint32_t)((PAIR ? 2 : 1) * steps * P.b_slot_bytes));
                     for (int s = 0; s < steps; ++s) {
                         int kcoord = s * P.KC;                                // TAP / RS order: (tap, chunk)
                         if (amode == AMODE_SLAB) {                          // SLAB order: (dx, chunk, dy)
@@ -563,7 +564,8 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                             const int dyi = s % 3, ch = s / 3;
                             kcoord = dyi * cin + ch * P.KC;
                         }
-                        ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)(blockIdx.x % q.n_tiles) * P.BN);
+                        if (PAIR) ptx::tma_load_2d_pair(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)pair_rank * (P.BN / 2));
+                        else      ptx::tma_load_2d(smem_b + (size_t)s * P.b_slot_bytes, &q.tmB, &b_res_bar, kcoord, (int)(blockIdx.x % q.n_tiles) * P.BN);
                     }
                 }
                 __syncwarp();
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                 if (PAIR) {                                   // both CTAs' slabs complete the LEADER's barrier
                                     if (pair_rank == 0) ptx::mbar_expect_tx(&full_a[ia], 2 * slab_bytes);
                                     ptx::tma_load_4d_pair(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
-                                                          tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
+                                                          one_slab ? tc.x0 : tc.x0 + dxi - 1, tc.y0 - 1, tc.b);
                                 } else {
                                     ptx::mbar_expect_tx(&full_a[ia], slab_bytes);
                                     ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC,
