@@ -128,7 +128,8 @@ struct Engine {
     int opt_convt_batch = 1;
     int opt_tb = 1;           // per-tap staged tiles may span two frames
     int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
-    int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N layers
+    int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N
+                              // layers, bit 3 resident-weight transposed convs (HBM-bound: measured neutral, off by default)
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
@@ -613,7 +614,8 @@ static View sub_view(const View& v, int choff, int C) {
     X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0) \
     X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 0) \
     X(2, false, false, true, AMODE_RS, EPI_OUTCONV, 2, 0) \
-    X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, true, AMODE_DXN, EPI_STORE, 2, 0)
+    X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, true, AMODE_DXN, EPI_STORE, 2, 0) \
+    X(2, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0)
 static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep, int kk, int pl) {
 #define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) \
     if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP) && kk == (KK) && pl == (PL)) \
@@ -730,9 +732,11 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // ... and the small-N layers whose weights are resident (row-shifted / dx-stacked staging): each CTA keeps half of
     // the weight rows, so the B operand read per MMA and SM halves (32 + N/8 instead of 32 + N/4 cycles), and one MMA
     // issuer drives two SMs, which halves the per-tile issue latency that paces these layers
-    const bool pair_res = (e.opt_pair & 4) != 0 && (rs || dxn) && descs.size() == 1 && e.opt_resident != 0 && Ntot == n_out &&
-                          (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV) && tiles_total0 % 2 == 0 && tiles_total0 >= 2 &&
-                          (size_t)steps * (BN / 2) * swz <= res_limit;
+    // (the transposed convolutions with resident weights too: one k-step per tile, so the issuer's per-tile latency is all there is)
+    const bool pair_res = descs.size() == 1 && e.opt_resident != 0 && Ntot == n_out && tiles_total0 % 2 == 0 && tiles_total0 >= 2 &&
+                          (size_t)steps * (BN / 2) * swz <= res_limit &&
+                          (((e.opt_pair & 4) != 0 && (rs || dxn) && (d0.epi == EPI_STORE || d0.epi == EPI_OUTCONV)) ||
+                           ((e.opt_pair & 8) != 0 && !slab && d0.epi == EPI_CONVT && BN % 32 == 0));
     const bool pair = pair_res || ((pair_slab || pair_tap) && d0.epi == EPI_STORE && (Ntot == BN || pair_tap) && BN >= 128 && tiles_total0 % 2 == 0 && tiles_total0 >= 2);
     P.pair_order = (pair && Ntot != BN) ? 1 : 0;                  // several N tiles: a pair walks two M tiles of one N tile
     P.b_slot_bytes = (pair ? BN / 2 : BN) * swz;

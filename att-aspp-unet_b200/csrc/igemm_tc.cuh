@@ -588,11 +588,11 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                             if (PAIR) {                                       // both CTAs' boxes complete the LEADER's barriers
                                 if (pair_rank == 0) {
                                     ptx::mbar_expect_tx(&full_a[ia], 2 * (uint32_t)P.a_slot_bytes);
-                                    ptx::mbar_expect_tx(&full_b[ib], 2 * (uint32_t)P.b_slot_bytes);
+                                    if (!res) ptx::mbar_expect_tx(&full_b[ib], 2 * (uint32_t)P.b_slot_bytes);
                                 }
                                 ptx::tma_load_4d_pair(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);
-                                ptx::tma_load_2d_pair(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC,
-                                                      tc.n0 + (int)pair_rank * (P.BN / 2));      // this CTA's half of the weight rows
+                                if (!res) ptx::tma_load_2d_pair(smem_b + (size_t)ib * P.b_slot_bytes, &q.tmB, &full_b[ib], s * P.KC,
+                                                                tc.n0 + (int)pair_rank * (P.BN / 2));   // this CTA's half of the weight rows
                             } else {
                                 ptx::mbar_expect_tx(&full_a[ia], (uint32_t)P.a_slot_bytes);
                                 ptx::tma_load_4d(smem_a + (size_t)ia * P.a_slot_bytes, &q.tmA, &full_a[ia], ch * P.KC, tc.x0 + dx, tc.y0 + dy, tc.b);

@@ -153,7 +153,9 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *              tile-shape search, un-split dx-stacked weights)
  *   "resident" 1/0 allow / forbid keeping a layer's whole weight matrix in shared memory
  *   "ctas" (0 auto, 1..2 CTAs per SM), "ng" (0 auto, 2 / 4 epilogue groups = TMEM stages), "cslots", "convt_batch", "lean"
- *   "pair"     CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers (default 3)
+ *   "pair"     CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight
+ *              small-N layers, bit 3 resident-weight transposed convolutions (default 7)
+ *   "tb"       1/0 per-tap staged tiles of small images may span two frames
  *   "spec"     1/0 use the kernel instantiations specialised per (staging mode, epilogue, K step, fused pool)
  *   "stem_tc"  1/0 uint8 frames run d1.0 on the tensor cores (0: packed-fp32 stem, as float frames always do)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue

@@ -286,6 +286,8 @@ OPTION_SETS = [
     {"dxn_full": 0},                # u2.conv.0 with its dx-stacked weights split in two N tiles
     {"spec": 0, "tb": 0},           # generic kernel instantiations only, one frame per tile
     {"pair": 1, "stem_tc": 0},      # CTA pairs for slab-staged layers only
+    {"pair": 15},                   # ... and for the resident-weight transposed convolutions too
+    {"pair": 4, "ng": 2},           # pairs for the resident-weight small-N layers only, two epilogue groups
 ]
 
 
