@@ -612,7 +612,7 @@ static View sub_view(const View& v, int choff, int C) {
     X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 1) \
     X(2, false, false, false, AMODE_TAP, EPI_GATE, 4, 0) X(2, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) \
     X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0) \
-    X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 0) \
+    X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 1) \
     X(2, false, false, true, AMODE_RS, EPI_OUTCONV, 2, 0) \
     X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, true, AMODE_DXN, EPI_STORE, 2, 0) \
     X(2, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0)
@@ -680,7 +680,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
               (size_t)9 * Cin * BN * 2 <= 112 * 1024;
     // measured A/B (B200, batch 28): with fused pooling and weights too large for two CTAs per SM (d2.1, 64 -> 64) the
     // dx-stacked form is 7 % faster; everywhere else row-shifted taps win or tie
-    if (rs && dxn && want_pool && (size_t)9 * Cin * BN * 2 > 64 * 1024 && e.opt_amode < 0) rs = false;
+    // (without CTA pairs; with them each CTA holds half of the weights, two clusters share an SM pair and row-shifted taps
+    // win there too: d2.1 -10 % against the paired dx-stacked form)
+    if (rs && dxn && want_pool && (size_t)9 * Cin * BN * 2 > 64 * 1024 && e.opt_amode < 0 && (e.opt_pair & 4) == 0) rs = false;
     if (rs) { dxn = false; n_out = BN; }
     if (dxn || rs) slab = true;                                    // shares the slab geometry code below
     P.amode = rs ? AMODE_RS : (dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP));
