@@ -32,8 +32,22 @@
 //                is what bounds the DXN layers whose K is small.
 //   With MT = 2 (SLAB, BN <= 128) a tile is two vertically adjacent 128-pixel blocks fed from one taller slab: every
 //   weight sub-block is used for two MMA groups, which halves the L2->SM weight traffic of the mid-size layers.
+//   Per-tap staged tiles of small images may span TB = 2 frames (the TMA boxes get a batch extent): the 35 x 46 bridge
+//   pads to 36 instead of 40 rows.
 // B operand (weights [N][K], K contiguous), own ring of `nB` slots of one (KC x BN) sub-block each -- or, when the
 //   whole weight matrix of the layer fits (`b_resident`), loaded ONCE per CTA and kept for every tile.
+//
+// CTA pairs (PAIR, cluster (2,1,1), tcgen05.*.cta_group::2): one M = 256 MMA spans two SMs -- each CTA stages its own 128
+// pixel rows of A and HALF of the rows of every weight sub-block (streamed or resident), the leader's elected lane issues
+// the instruction for both, accumulators land in each CTA's own TMEM, one multicast commit frees both CTAs' ring slots.
+// It halves the weight bytes every SM pulls from L2 (what bounded the N = 128 slab layers), halves the B operand's
+// shared-memory read per MMA (32 + N/8 instead of 32 + N/4 cycles: the small-N layers) and lets one issuer warp pace
+// two SMs.  Launches with several N tiles walk the tiles pairwise (`pair_order`) so that a pair shares its N tile.
+//
+// Instantiations: the template parameters AM / EP / KKT / PL fix the staging mode, the epilogue, the MMAs per sub-block
+// and the fused MaxPool at compile time for the bf16 hot path (a third of the generic kernel's 110 KB of SASS: the
+// single-warp roles miss the instruction cache less and skip the uniform mode branches); -1 = decided at run time
+// from IgemmParams, which every plan, fp16 storage and the forced-plan parity tests can use.
 //
 // Warp roles (64 + 128*NG threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run warp-uniform,
 // the asynchronous instructions under elect.sync), then NG in {2, 4} epilogue groups of four warps (one warp per TMEM

@@ -32,6 +32,27 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == bound, f"ctypes table and header differ: {declared ^ bound}"
 
 
+def test_every_planner_option_is_documented_in_the_header():
+    """include/aau.h lists the names aau_set_option accepts; the table in the engine is the source of truth."""
+    eng = (ROOT / "att-aspp-unet_b200" / "csrc" / "aau_engine.cu").read_text()
+    table = eng[eng.index("plan_options[] = {"):]
+    table = table[:table.index("};")]
+    names = set(re.findall(r'\{"(\w+)", &e\.opt_', table))
+    assert len(names) >= 20, names
+    doc = (ROOT / "include" / "aau.h").read_text()
+    doc = doc[doc.index("Planner options"):doc.index("int aau_set_option")]
+    missing = sorted(n for n in names if f'"{n}"' not in doc)
+    assert not missing, f"options accepted by aau_set_option but not described in include/aau.h: {missing}"
+
+
+def test_product_sources_never_reach_for_the_oracle_or_a_cpu_path():
+    """The oracle is test infrastructure: nothing under the package (or the C ABI sources) may import / execute it."""
+    pkg = ROOT / "att-aspp-unet_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        text = f.read_text()
+        assert "aau_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f.name
+
+
 def test_create_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
