@@ -204,7 +204,7 @@ def run_engine(args):
     logits_all = torch.empty((N_FRAMES, 1, H, W), dtype=torch.float32, device=dev)
     areas = torch.zeros(N_FRAMES, dtype=torch.int32, device=dev)
     best = torch.zeros(2, dtype=torch.int32, device=dev)
-    thr = seg.PROB_THRESHOLD
+    thr = args.prob_thr
 
     def device_step():
         for s in starts:
@@ -240,13 +240,13 @@ def run_engine(args):
     # ---------------- end-to-end arm (public API, pinned host input, results back on the host)
     res = None
     for _ in range(max(1, min(args.warmup, 2))):
-        res = seg.segment_sweep(vol_pinned)
+        res = seg.segment_sweep(vol_pinned, prob_thr=thr)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res = seg.segment_sweep(vol_pinned)
+        res = seg.segment_sweep(vol_pinned, prob_thr=thr)
         if world > 1:
             gather_areas(np.array([res["best_area"], res["best_idx"]], np.int32), 2 * world, dev)   # host gather of per-case scores
     e1.record()
@@ -317,7 +317,8 @@ def run_engine(args):
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(res["h2d_bytes"]), "d2h_bytes_per_step": int(res["d2h_bytes"]),
                     "api": "FetalAbdomenSegmentation.segment_sweep(pinned uint8 sweep) -> areas, best index, post-processed mask"},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roof,
-            "selected_frame": {"device_arm": best_dev[0], "e2e_arm": res["best_idx"], "area": res["best_area"]}}
+            "selected_frame": {"device_arm": best_dev[0], "e2e_arm": res["best_idx"], "area": res["best_area"], "prob_thr": thr,
+                               "distinct_areas": int(len(np.unique(areas.cpu().numpy())))}}
     if world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, frames=args.cpu_frames)
     emit(line)
@@ -336,6 +337,9 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (amode, resident, ctas)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample of the engine arm")
+    ap.add_argument("--prob-thr", type=float, default=0.5,
+                    help="probability threshold of the per-frame area score (0.5 = the pipeline CLI's binarisation; the wrapper's "
+                         "0.05 marks every pixel of a random-weight network, so every frame would tie at the full-frame area)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
