@@ -103,6 +103,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = ("config[1]: one 840-frame 744x562 uint8 sweep per GPU, AttentionASPPUNet base_c=32, BN-calibrated random weights, "
+            "forward + sigmoid/threshold/area + first-max argmax")
+
+
 def make_weights():
     import aau_oracle as O
     cfg = O.NetCfg(base_c=BASE_C)
@@ -138,7 +142,7 @@ def run_reference(args):
     def step():
         logits = O.forward(sd, x, cfg)
         prob = torch.sigmoid(logits)[:, 0].numpy()
-        m3 = O.postprocess(prob)
+        m3 = O.postprocess(prob, thr=args.prob_thr)
         return O.select_fetal_abdomen_mask_and_frame(m3)
 
     for _ in range(args.warmup):
@@ -152,7 +156,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config[1]: 840-frame 744x562 sweep, base_c=32 (bounded CPU sample)", "frames_per_step": frames},
+            "config": {"workload": WORKLOAD, "frames_per_step": frames, "note": "bounded CPU sample of that workload"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count(), "torch": torch.__version__},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -310,8 +314,7 @@ def run_engine(args):
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": "config[1]: one 840-frame 744x562 uint8 sweep per GPU, AttentionASPPUNet base_c=32, BN-calibrated random weights, "
-                                   "forward + sigmoid/threshold/area + first-max argmax" + (" (config[2]: one case per GPU, host gather)" if world > 1 else ""),
+            "config": {"workload": WORKLOAD + (" (config[2]: one case per GPU, host gather)" if world > 1 else ""),
                        "frames_per_step_per_gpu": N_FRAMES, "batch": B, "act_dtype": args.dtype, "l2": "inputs larger than L2 (351 MB sweep; >6 GB of activations per batch)",
                        "parallelism": f"dp{world} by case, no collective on the forward path"},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(res["h2d_bytes"]), "d2h_bytes_per_step": int(res["d2h_bytes"]),
