@@ -323,7 +323,7 @@ def run_engine(args):
             "selected_frame": {"device_arm": best_dev[0], "e2e_arm": res["best_idx"], "area": res["best_area"], "prob_thr": thr,
                                "distinct_areas": int(len(np.unique(areas.cpu().numpy())))}}
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, frames=args.cpu_frames)
+        line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, frames=args.cpu_frames, reps=5 if args.cpu_frames >= 8 else 2)   # ~10 s of CPU work by default
     emit(line)
     if world > 1:
         dist.destroy_process_group()
