@@ -114,7 +114,13 @@ __host__ inline FastDiv make_fastdiv(uint32_t d) {
     f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
     return f;
 }
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(n, f.mul) + n) >> f.shr; }
+__host__ __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) {
+#ifdef __CUDA_ARCH__
+    return (__umulhi(n, f.mul) + n) >> f.shr;
+#else
+    return ((uint32_t)(((uint64_t)n * f.mul) >> 32) + n) >> f.shr;   // host twin: tests/decode_check.cu walks the tile maps on the CPU
+#endif
+}
 
 struct alignas(64) IgemmProblem {
     CUtensorMap tmA;        // activations, 4-D (C, W, H, B)
@@ -210,7 +216,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 struct TileCoord { int pi, b, y0, x0, n0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
+__host__ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
     TileCoord tc;
     int pi = 0;
 #pragma unroll
@@ -248,7 +254,7 @@ struct TileIter {
     int s_nt, s_x, s_y, s_b;  // digits of the stride
     int tiles_x, tiles_y, n_tiles;
     bool incremental;
-    __device__ __forceinline__ void init(const IgemmParams& P, int first, int stride_) {
+    __host__ __device__ __forceinline__ void init(const IgemmParams& P, int first, int stride_) {
         t = first; stride = stride_; total = P.total_tiles;
         incremental = P.nprob == 1 && P.tile_iter != 0 && P.pair_order == 0;
         if (incremental) {
@@ -267,8 +273,8 @@ struct TileIter {
             digits(stride_, s_nt, s_x, s_y, s_b);
         }
     }
-    __device__ __forceinline__ bool valid() const { return t < total; }
-    __device__ __forceinline__ void next() {
+    __host__ __device__ __forceinline__ bool valid() const { return t < total; }
+    __host__ __device__ __forceinline__ void next() {
         t += stride;
         if (incremental) {
             nt += s_nt;
@@ -283,7 +289,7 @@ struct TileIter {
             b += s_b + c;
         }
     }
-    __device__ __forceinline__ TileCoord coord(const IgemmParams& P) const {
+    __host__ __device__ __forceinline__ TileCoord coord(const IgemmParams& P) const {
         if (!incremental) return decode_tile(P, t);
         TileCoord tc;
         tc.pi = 0;

@@ -53,6 +53,22 @@ def test_product_sources_never_reach_for_the_oracle_or_a_cpu_path():
         assert "aau_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f.name
 
 
+def test_tile_maps_enumerate_every_tile_once():
+    """decode_tile / TileIter of the kernel header are __host__ __device__: tests/decode_check.cu walks them on the CPU for
+    the planner's launch geometries (stacked M-blocks, several N tiles, several problems, two-frame tiles, CTA-pair order)."""
+    import shutil, subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = ROOT / "tests" / "_build"
+    out.mkdir(exist_ok=True)
+    exe = out / "decode_check"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "decode_check.cu")],
+                   check=True, cwd=str(ROOT))
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok (0 failures)" in r.stdout, r.stdout[-2000:]
+
+
 def test_create_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
