@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("AAU_LIB", _HERE / "libaau.so"))
 AAU_VARIANT_PIPELINE, AAU_VARIANT_ABLATION = 0, 1
 AAU_ACT_BF16, AAU_ACT_FP16 = 0, 1
 AAU_X_F32, AAU_X_U8 = 0, 1
-AAU_IN_LOGITS, AAU_IN_PROB, AAU_IN_U8 = 0, 1, 2
+AAU_IN_LOGITS, AAU_IN_PROB, AAU_IN_U8, AAU_IN_LOGIT_CUT = 0, 1, 2, 3
 
 
 class AauConfig(C.Structure):

@@ -135,12 +135,14 @@ class AttentionASPPUNet(nn.Module):
     (attention_aspp_unet_pipeline_stage.py:112); ``AttentionASPPUNet(in_ch=1, num_classes=1, base=16)`` is how the
     ROI wrapper spells it (model_attention_aspp.py:36); passing any of ``use_att / use_aspp / att_depth`` (or
     ``variant="ablation"``) builds the ablation twin (test_ablation.py:169-177) whose forward returns
-    ``(logits, [psi3, psi2])``.  ``act_dtype`` ("bf16" default, "fp16") is the storage type of activations and packed
-    weights inside the engine; accumulation and all epilogue math are fp32.
+    ``(logits, [psi3, psi2])``.  ``act_dtype`` is the 16-bit storage type of activations and packed weights inside
+    the engine -- "fp16" (default: 11 significant bits, the only 16-bit type that meets the 2e-2 / 99.9 % parity bar on
+    BN-calibrated weights) or "bf16" (8 bits; same kernels, same speed); the tensor cores accumulate
+    in fp32 and all epilogue math is fp32 in both.  Values beyond the fp16 range saturate to +-65504 instead of becoming inf.
     """
 
     def __init__(self, in_channels: int = 1, num_classes: int = 1, base_c: int = 32, use_att=_UNSET, use_aspp=_UNSET,
-                 att_depth=_UNSET, *, in_ch=None, base=None, variant: str | None = None, act_dtype: str = "bf16"):
+                 att_depth=_UNSET, *, in_ch=None, base=None, variant: str | None = None, act_dtype: str = "fp16"):
         super().__init__()
         if in_ch is not None:
             in_channels = in_ch

@@ -10,6 +10,7 @@
 #include "../../include/aau.h"
 #include "hbm_kernels.cuh"
 #include "stem_tc.cuh"
+#include "igemm_inst.cuh"
 
 #include <cudaTypedefs.h>
 #include <algorithm>
@@ -117,6 +118,8 @@ struct Engine {
     uint16_t* d_stem_wB = nullptr;                     // [c][16] K-major, w*s/255 in the activation type (tensor-core stem)
     float *d_poolT = nullptr, *d_poolb = nullptr, *d_projT = nullptr, *d_projb = nullptr;
     std::vector<void*> dev_allocs;
+    std::map<std::pair<int, int>, float*> fix_coef;   // bilinear fix-up blend tables by (in, out) size, shared by every plan
+    float cut_thr = NAN, cut_val = 0.f;                // last (probability threshold -> logit cutoff) pair
     std::vector<std::unique_ptr<Plan>> plans;
     int* d_err = nullptr;
     cudaStream_t side_stream = nullptr;               // ASPP image-pooling branch (fork / join around the conv branches)
@@ -264,6 +267,7 @@ struct Prep {
 
 static uint16_t to16(float f, bool fp16) {
     if (fp16) {
+        f = std::max(-65504.f, std::min(65504.f, f));                // saturate like the kernels' conversions do
         __half h = __float2half_rn(f);
         return *reinterpret_cast<uint16_t*>(&h);
     }
@@ -343,6 +347,7 @@ static int commit_weights(Engine& e) {
     for (void* p : e.dev_allocs) cudaFree(p);
     e.dev_allocs.clear();
     e.gw.clear();
+    e.fix_coef.clear();
     e.plans.clear();
     e.last_plan = nullptr;
     e.committed = false;
@@ -597,34 +602,14 @@ static View sub_view(const View& v, int choff, int C) {
     return s;
 }
 
-// Instantiations of igemm_tc_kernel.  The generic ones (AM = EP = -1) branch on the staging mode and epilogue at run time
-// and serve every plan; the bf16 hot path additionally gets instantiations with both fixed at compile time -- a third of
-// the code size each, so the single-warp roles miss the instruction cache less and skip the uniform mode branches.
-#define AAU_IGEMM_GENERIC(X) \
-    X(2, false, false, false, -1, -1, -1, -1) X(2, true, false, false, -1, -1, -1, -1) X(4, false, false, false, -1, -1, -1, -1) X(4, true, false, false, -1, -1, -1, -1) \
-    X(2, false, true, false, -1, -1, -1, -1) X(2, true, true, false, -1, -1, -1, -1) X(2, false, false, true, -1, -1, -1, -1) X(2, true, false, true, -1, -1, -1, -1) \
-    X(2, false, true, true, -1, -1, -1, -1) X(2, true, true, true, -1, -1, -1, -1) X(4, false, false, true, -1, -1, -1, -1) X(4, true, false, true, -1, -1, -1, -1)
-// (NG, fp16, multi-problem, CTA pair, staging mode, epilogue, MMAs per sub-block = KC / 16, fused MaxPool)
-#define AAU_IGEMM_SPECIALISED(X) \
-    X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, false, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, false, AMODE_RS, EPI_STORE, 4, 0) \
-    X(2, false, false, false, AMODE_RS, EPI_OUTCONV, 2, 0) \
-    X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, false, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, false, AMODE_DXN, EPI_STORE, 2, 0) \
-    X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_SLAB, EPI_STORE, 4, 1) \
-    X(2, false, false, false, AMODE_TAP, EPI_GATE, 4, 0) X(2, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, false, AMODE_TAP, EPI_CONVT, 4, 0) \
-    X(2, false, false, false, AMODE_TAP, EPI_CONVTFIX, 4, 0) X(2, false, false, true, AMODE_TAP, EPI_STORE, 4, 0) X(2, false, true, true, AMODE_TAP, EPI_STORE, 4, 0) \
-    X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, false, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 0) X(4, false, false, true, AMODE_RS, EPI_STORE, 4, 1) \
-    X(2, false, false, true, AMODE_RS, EPI_OUTCONV, 2, 0) \
-    X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, false, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, false, false, true, AMODE_DXN, EPI_STORE, 2, 0) \
-    X(2, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0) X(4, false, false, true, AMODE_TAP, EPI_CONVT, 4, 0)
+// Kernel lookup over the instantiation tables (igemm_inst.cuh; one translation unit per table so that they compile in
+// parallel): the specialised instantiation of the storage type when there is one, else the generic one.
 static const void* igemm_kernel(int ng, bool f16, bool multi, bool pair, int am, int ep, int kk, int pl) {
-#define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) \
-    if (ng == NG && f16 == F16 && multi == MULTI && pair == PAIR && am == (AM) && ep == (EP) && kk == (KK) && pl == (PL)) \
-        return (const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP, KK, PL>;
-    AAU_IGEMM_SPECIALISED(X)
-    if (am != -1 || ep != -1 || kk != -1 || pl != -1) return igemm_kernel(ng, f16, multi, pair, -1, -1, -1, -1);
-    AAU_IGEMM_GENERIC(X)
-#undef X
-    return nullptr;
+    if (am != -1 || ep != -1 || kk != -1 || pl != -1) {
+        const void* fn = f16 ? igemm_spec_fp16(ng, multi, pair, am, ep, kk, pl) : igemm_spec_bf16(ng, multi, pair, am, ep, kk, pl);
+        if (fn) return fn;
+    }
+    return f16 ? igemm_generic_fp16(ng, multi, pair) : igemm_generic_bf16(ng, multi, pair);
 }
 
 // Builds one persistent-GEMM launch over up to 4 problems sharing input geometry, BN and KC.
@@ -1194,8 +1179,16 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             std::vector<float> coef;
             const GemmW* gwf = prep_upfix(e, l, axis, fcc);
             if (gwf && fix_coefficients(axis == 0 ? 2 * Hs[l + 1] : 2 * Ws[l + 1], axis == 0 ? Hs[l] : Ws[l], coef)) {
+                // one table per (in, out) size for the life of the weights: plan rebuilds (set_option, a new workspace,
+                // more than 8 cached shapes) must not allocate
+                const std::pair<int, int> ck(axis == 0 ? 2 * Hs[l + 1] : 2 * Ws[l + 1], axis == 0 ? Hs[l] : Ws[l]);
                 float* dcoef = nullptr;
-                if (upload(e, coef, &dcoef) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "fix-up coefficient upload failed");
+                auto cit = e.fix_coef.find(ck);
+                if (cit != e.fix_coef.end()) dcoef = cit->second;
+                else {
+                    if (upload(e, coef, &dcoef) != cudaSuccess) return e.fail(AAU_ERR_CUDA, "fix-up coefficient upload failed");
+                    e.fix_coef[ck] = dcoef;
+                }
                 ConvDesc d;
                 d.w = gwf;
                 d.in = gin; d.out = gdst; d.epi = EPI_CONVTFIX; d.relu = 0; d.convt_cout = ch[l];
@@ -1311,10 +1304,10 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     };
     bool raised = raise_smem((const void*)stem_tc_kernel<false>) && raise_smem((const void*)stem_tc_kernel<true>);
-#define X(NG, F16, MULTI, PAIR, AM, EP, KK, PL) raised = raised && raise_smem((const void*)igemm_tc_kernel<NG, F16, MULTI, PAIR, AM, EP, KK, PL>);
-    AAU_IGEMM_GENERIC(X)
-    AAU_IGEMM_SPECIALISED(X)
-#undef X
+    {
+        const int lim = 232448 - 6144;
+        raised = raised && igemm_generic_bf16_raise(lim) && igemm_generic_fp16_raise(lim) && igemm_spec_bf16_raise(lim) && igemm_spec_fp16_raise(lim);
+    }
     if (!raised) {
         g_create_error = "cannot raise the dynamic shared memory limit";
         delete h;
@@ -1454,6 +1447,31 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
     return AAU_OK;
 }
 
+// Largest fp32 value l with sigmoid(l) <= t, sigmoid evaluated in double and rounded once to fp32 (a correctly rounded fp32
+// sigmoid): `sigmoid(x) > t` is then exactly `x > cutoff` (monotone; SURVEY.md identity i7).  Bisection over the ordered
+// integer image of the fp32 number line; t >= 1 gives +inf (nothing passes), t < 0 gives -inf (everything finite passes).
+static float logit_cutoff(float t) {
+    auto key_to_float = [](int64_t k) {
+        uint32_t b = k >= 0 ? (uint32_t)k : (0x80000000u | (uint32_t)(-k));
+        float f;
+        memcpy(&f, &b, 4);
+        return f;
+    };
+    auto passes = [&](int64_t k) {
+        const double l = (double)key_to_float(k);
+        return (float)(1.0 / (1.0 + std::exp(-l))) > t;
+    };
+    const int64_t inf_key = 0x7f800000;
+    int64_t lo = -inf_key, hi = inf_key;                           // passes(lo) false (sigmoid(-inf) = 0) unless t < 0
+    if (passes(lo)) return key_to_float(lo);
+    if (!passes(hi)) return key_to_float(hi);
+    while (hi - lo > 1) {                                          // invariant: !passes(lo) && passes(hi)
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (passes(mid)) hi = mid; else lo = mid;
+    }
+    return key_to_float(lo);
+}
+
 int aau_frame_scores(aau_handle* h, const void* logits, int input_kind, int N, int H, int W, float prob_thr, int32_t* areas,
                      int32_t* best, uint8_t* mask, void* stream) {
     if (!h) return AAU_ERR_INVALID;
@@ -1467,8 +1485,13 @@ int aau_frame_scores(aau_handle* h, const void* logits, int input_kind, int N, i
     if (input_kind == AAU_IN_U8) {
         if ((long long)HW * 255 > 0x7fffffffLL) return e.fail(AAU_ERR_INVALID, "frame too large for 32-bit byte sums");
         frame_sum_u8_kernel<<<dim3(gx, N), 256, 0, s>>>((const uint8_t*)logits, HW, areas, mask);
-    } else if (input_kind == AAU_IN_LOGITS || input_kind == AAU_IN_PROB) {
-        frame_area_kernel<<<dim3(gx, N), 256, 0, s>>>((const float*)logits, input_kind == AAU_IN_PROB ? 1 : 0, HW, prob_thr, areas, mask);
+    } else if (input_kind == AAU_IN_LOGITS || input_kind == AAU_IN_PROB || input_kind == AAU_IN_LOGIT_CUT) {
+        float cut = prob_thr;                                        // probabilities and caller-supplied cutoffs compare as they are
+        if (input_kind == AAU_IN_LOGITS) {
+            if (e.cut_thr != prob_thr) { e.cut_val = logit_cutoff(prob_thr); e.cut_thr = prob_thr; }
+            cut = e.cut_val;
+        }
+        frame_area_kernel<<<dim3(gx, N), 256, 0, s>>>((const float*)logits, input_kind == AAU_IN_PROB ? 1 : 0, HW, cut, areas, mask);
     } else {
         return e.fail(AAU_ERR_INVALID, "unknown input_kind");
     }
@@ -1596,8 +1619,8 @@ int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel
 int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H, int* W, int* C, int* ld, int* choff) {
     if (!h || !name) return AAU_ERR_INVALID;
     Engine& e = h->e;
-    if (e.plans.empty()) return e.fail(AAU_ERR_STATE, "no forward has run yet");
-    Plan& p = *e.plans.back();
+    if (!e.last_plan) return e.fail(AAU_ERR_STATE, "no forward has run yet");
+    Plan& p = *e.last_plan;
     auto it = p.named.find(name);
     if (it == p.named.end() || !it->second.p) return e.fail(AAU_ERR_INVALID, std::string("unknown tensor ") + name);
     const View& v = it->second;

@@ -179,11 +179,13 @@ __global__ void __launch_bounds__(256) gap_partial_kernel(const uint8_t* __restr
     extern __shared__ float s_buf[];                 // [lanes][Cin]
     const int b = blockIdx.y, sp = blockIdx.x;
     const int pairs = Cin >> 1;
-    const int lanes = blockDim.x / pairs;
-    const int pl = threadIdx.x / pairs, cp = threadIdx.x % pairs;
+    // pixel lanes: 256 / pairs threads share a channel pair; with more than 256 pairs (base_c >= 80) every thread walks
+    // several channel pairs over ALL pixels of the slice instead (lanes == 1)
+    const int lanes = max(1, (int)blockDim.x / pairs);
     const int per = (HW + splits - 1) / splits;
     const int p0 = sp * per, p1 = min(HW, p0 + per);
-    if (pl < lanes) {
+    for (int slot = threadIdx.x; slot < lanes * pairs; slot += blockDim.x) {
+        const int pl = slot / pairs, cp = slot - pl * pairs;
         float s0 = 0.f, s1 = 0.f;
         const uint32_t* base = reinterpret_cast<const uint32_t*>(x + (size_t)b * HW * Cin * 2) + cp;
         for (int p = p0 + pl; p < p1; p += lanes) {
@@ -320,19 +322,20 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Selection head: per-frame sigmoid / threshold / mask area, then first-max argmax over frames
+// Selection head: per-frame threshold / mask area, then first-max argmax over frames
 // (model_attention_aspp.py:54 sigmoid, :71 `prob > 0.05`, :74 / :94 `sum((1,2)).argmax()`).
-// Each thread reads float4 logits, evaluates sigmoid in fp32 exactly as `1/(1+exp(-x))`, counts, then the counts
-// are reduced with warp shuffles, one shared-memory hop per block and ONE integer atomic per block, so the result
-// is exact and order independent.  The optional mask output is the uint8 {0,1} volume the reference builds.
+// sigmoid is monotone, so `sigmoid(l) > t` is `l > cut` for ONE fp32 cutoff (SURVEY.md identity i7): the host finds it by
+// bisection over the fp32 number line (aau_engine.cu: logit_cutoff -- correctly rounded fp32 sigmoid; the Python layer passes
+// the cutoff of the HOST's own torch.sigmoid instead, AAU_IN_LOGIT_CUT), and no transcendental runs per pixel: the decision
+// is a pure comparison, bit exact.  Each thread reads float4 values and counts; counts are reduced with warp shuffles, one
+// shared-memory hop per block and ONE integer atomic per block, so the result is exact and order independent.  The
+// optional mask output is the uint8 {0,1} volume the reference builds.
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ int above(float v, float thr, int is_prob) {
-    return (is_prob ? v : 1.f / (1.f + expf(-v))) > thr;
-}
+__device__ __forceinline__ int above(float v, float cut, int /*is_prob*/) { return v > cut; }
 __global__ void __launch_bounds__(256) frame_area_kernel(const float* __restrict__ logits, int is_prob, int HW, float thr,
                                                          int* __restrict__ areas, uint8_t* __restrict__ mask) {
     const int frame = blockIdx.y;

@@ -172,10 +172,12 @@ struct alignas(64) IgemmParams {
 };
 
 // ---- 16-bit activation helpers (bf16 by default, fp16 as the higher-precision storage option) -------------
+// fp16 storage saturates to +-65504 (cvt.satfinite) instead of overflowing to inf: one instruction either way
 __device__ __forceinline__ uint32_t pack2(float a, float b, int is_fp16) {
     if (is_fp16) {
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -184,7 +186,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_fp16) {
 template <bool F16>
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
     uint32_t r;
-    if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     else     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }

@@ -32,7 +32,7 @@ except ImportError:                                     # package-style import
     from .attention_aspp_unet import AttentionASPPUNet  # type: ignore
 
 __all__ = ["FetalAbdomenSegmentation", "select_fetal_abdomen_mask_and_frame", "merge_shard_scores", "largest_component",
-           "preprocess_sweep", "load_image_file_as_array", "crop_roi_224"]
+           "preprocess_sweep", "load_image_file_as_array", "crop_roi_224", "logit_cutoff"]
 
 ROI = 224                                               # model_attention_aspp.py:20-30
 N_SAMPLED_FRAMES = 128                                  # model_attention_aspp.py:45
@@ -104,6 +104,45 @@ def merge_shard_scores(shard_areas: Sequence[np.ndarray]) -> Tuple[np.ndarray, i
     return areas, int(areas.argmax())
 
 
+_CUTOFFS = {}
+
+
+def logit_cutoff(prob_thr: float) -> float:
+    """The fp32 logit ``c`` with ``torch.sigmoid(l) > prob_thr  <=>  l > c`` for THIS host's ``torch.sigmoid`` (the
+    reference's own arithmetic, model_attention_aspp.py:54,71): sigmoid is monotone, so the threshold on the probability
+    is a threshold on the logit, found once per threshold by bisection over the fp32 number line (SURVEY.md identity
+    i7).  The device then only compares (``AAU_IN_LOGIT_CUT``): no transcendental per pixel, and the decision is the
+    one the reference's fp32 sigmoid makes, bit for bit."""
+    t = float(np.float32(prob_thr))
+    c = _CUTOFFS.get(t)
+    if c is not None:
+        return c
+
+    def to_float(k: int) -> float:                       # ordered integer image of the fp32 number line
+        bits = k if k >= 0 else (0x80000000 | (-k))
+        return float(np.array([bits], np.uint32).view(np.float32)[0])
+
+    def passes(k: int) -> bool:                          # 64 copies: the vectorised ATen kernel, not its scalar tail
+        x = torch.full((64,), to_float(k), dtype=torch.float32)
+        return bool((torch.sigmoid(x).numpy() > np.float32(t))[0])
+
+    lo, hi = -0x7f800000, 0x7f800000
+    if passes(lo):
+        c = float("-inf")
+    elif not passes(hi):
+        c = float("inf")
+    else:
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if passes(mid):
+                hi = mid
+            else:
+                lo = mid
+        c = to_float(lo)
+    _CUTOFFS[t] = c
+    return c
+
+
 class _Scores:
     """Device-side threshold / area / arg-max through libaau (aau_frame_scores, aau_best_frame)."""
 
@@ -114,6 +153,8 @@ class _Scores:
     def run(self, values: torch.Tensor, kind: int, thr: float, areas: torch.Tensor, best: Optional[torch.Tensor],
             mask: Optional[torch.Tensor]):
         n, h, w = values.shape
+        if kind == _capi.AAU_IN_LOGITS:                   # threshold in logit space, calibrated on the host's sigmoid
+            kind, thr = _capi.AAU_IN_LOGIT_CUT, logit_cutoff(thr)
         st = _capi.lib().aau_frame_scores(self.net.engine_handle(), values.data_ptr(), kind, n, h, w, C.c_float(thr), areas.data_ptr(),
                                           best.data_ptr() if best is not None else None, mask.data_ptr() if mask is not None else None,
                                           torch.cuda.current_stream(self.device).cuda_stream)
@@ -134,18 +175,22 @@ class FetalAbdomenSegmentation:
 
     PROB_THRESHOLD = 0.05                                  # model_attention_aspp.py:71
 
+    DEFAULT_CHECKPOINT = "checkpoints/best_model.pth"      # model_attention_aspp.py:34
+
     def __init__(self, checkpoint_path: Optional[str] = None, *, net: Optional[AttentionASPPUNet] = None, base: int = 16,
-                 device: str | torch.device = "cuda", batch: int = 56, act_dtype: str = "bf16"):
+                 device: str | torch.device = "cuda", batch: int = 56, act_dtype: str = "fp16"):
         if not torch.cuda.is_available():
             raise RuntimeError("FetalAbdomenSegmentation (B200 engine) needs a CUDA device; there is no CPU fallback")
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         if net is None:
+            # as the reference (model_attention_aspp.py:34-37): the checkpoint is mandatory -- `torch.load` raises when the
+            # file is missing; a network with random weights is never built silently (pass `net=` to bring your own)
+            path = self.DEFAULT_CHECKPOINT if checkpoint_path is None else checkpoint_path
             net = AttentionASPPUNet(in_ch=1, num_classes=1, base=base, act_dtype=act_dtype)
-            if checkpoint_path is not None:
-                miss, unexp = net.load_state_dict(torch.load(checkpoint_path, map_location="cpu"), strict=False)
-                print(f"[DEBUG] load_state — missing:{len(miss)} unexpected:{len(unexp)}")
+            miss, unexp = net.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
+            print(f"[DEBUG] load_state — missing:{len(miss)} unexpected:{len(unexp)}")
         self.net = net.eval()
         self.batch = int(batch)
         self._scores = _Scores(self.net, self.device)
@@ -193,8 +238,8 @@ class FetalAbdomenSegmentation:
         is_u8 = vol.dtype == torch.uint8
         if not is_u8:
             vol = vol.float()
-        areas = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
-        best = torch.zeros(2, dtype=torch.int32, device=dev)
+        scores = torch.zeros(max(n, 1) + 2, dtype=torch.int32, device=dev)   # areas[n] | {best index, best area}: ONE D2H copy
+        areas, best = scores[: max(n, 1)], scores[max(n, 1):]
         B = max(1, min(self.batch, n))
         # every frame's logits stay resident (1.67 MB per 562x744 frame; 1.4 GB per 840-frame sweep of 180 GB)
         if getattr(self, "_logits_all", None) is None or self._logits_all.shape != (max(n, 1), 1, H, W):
@@ -205,10 +250,13 @@ class FetalAbdomenSegmentation:
         if self._pinned is None or self._pinned.shape != torch.Size(shape) or self._pinned.dtype != vol.dtype:
             self._pinned = torch.empty(shape, dtype=vol.dtype).pin_memory()
             self._staging = torch.empty(shape, dtype=vol.dtype, device=dev)
-        copy_stream = torch.cuda.Stream(device=dev)
+        if getattr(self, "_copy_stream", None) is None:                # stream and events live as long as the wrapper
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._events = [torch.cuda.Event() for _ in range(4)]
+        copy_stream = self._copy_stream
         main = torch.cuda.current_stream(dev)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        copy_stream.wait_stream(main)                                   # a previous call's kernels are done with the staging slots
+        ready, consumed = self._events[:2], self._events[2:]
         h2d = 0
         starts = list(range(0, n, B))
 
@@ -253,8 +301,9 @@ class FetalAbdomenSegmentation:
             out.update(areas=np.zeros(0, np.int32), best_idx=-1, best_area=0, mask=np.zeros((H, W), np.uint8), d2h_bytes=0)
             return out
         self._scores.best(areas[:n], best)
-        host_areas = areas[:n].cpu().numpy()                 # D2H: 4*n bytes, synchronises
-        bi, ba = [int(v) for v in best.cpu().numpy()]
+        host_scores = scores.cpu().numpy()                   # D2H: 4*n + 8 bytes in one copy, synchronises
+        host_areas = host_scores[:n].copy()
+        bi, ba = int(host_scores[-2]), int(host_scores[-1])
         out.update(areas=host_areas, best_area=ba, best_local=bi, d2h_bytes=4 * n + 8)
         if not finalize:
             return out

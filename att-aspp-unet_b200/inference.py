@@ -2,7 +2,7 @@
 
 Mirror of the reference's ``inference.py`` (run(): :50-133, write_array_as_image_file: :208-254,
 convert_2d_mask_to_3d: :257-273, write_json_file: :136-139, get_image_file_path: :196-199) driving the B200
-engine.  Environment: ``CASE_ID`` (output file stem, default ``output``), ``AAU_CHECKPOINT`` (state dict to load),
+engine.  Environment: ``CASE_ID`` (output file stem, default ``output``), ``AAU_CHECKPOINT`` (state dict to load; default ``checkpoints/best_model.pth`` as the reference, a missing file raises),
 ``AAU_BASE_C`` (default 16, the wrapper's ``base``), ``AAU_SWEEP_MODE``:
 
 * ``roi224`` (default) -- the reference wrapper's recipe: 128 sampled frames, 224x224 ROI per frame, paste back
@@ -87,7 +87,9 @@ def run(case_id: str | None = None, *, algorithm: FetalAbdomenSegmentation | Non
     if not paths:
         raise FileNotFoundError(f"no .mha / .tiff sweep under {input_path / 'images/stacked-fetal-ultrasound'}")
     if algorithm is None:
-        algorithm = FetalAbdomenSegmentation(os.getenv("AAU_CHECKPOINT"), base=int(os.getenv("AAU_BASE_C", "16")))
+        # AAU_CHECKPOINT unset -> the reference's default path; a missing file raises (never random weights)
+        algorithm = FetalAbdomenSegmentation(os.getenv("AAU_CHECKPOINT") or FetalAbdomenSegmentation.DEFAULT_CHECKPOINT,
+                                             base=int(os.getenv("AAU_BASE_C", "16")))
     sweep, _ = read_mha(paths[0])
     n_frames, ref_h, ref_w = sweep.shape
     if mode == "full":

@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """Headline benchmark: frames/sec of the AttentionASPPUNet forward + per-frame score + best-frame selection on a
-synthetic ACOUSLIC-style sweep (840 frames of 744x562, base_c=32) -- BASELINE.json `metric`, config[1] at N=1 and
+synthetic ACOUSLIC-style sweep (840 distinct frames of 744x562, base_c=32) -- BASELINE.json `metric`, config[1] at N=1 and
 config[2] (one sweep per GPU, sharded by case, host gather of scores) at N>1.
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA engine (libaau.so)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (CPU oracle)
+    torchrun ... bench.py --gpus N --split sweep             # ONE sweep split by contiguous frame blocks over N GPUs (strong scaling)
 
 A step = one pass of the hot path over one sweep.  `value` = frames of all ranks / max-over-ranks device time with
 the uint8 sweep already resident in HBM; `e2e` = the same through the public host API
 (FetalAbdomenSegmentation.segment_sweep) from pinned host memory, H2D copies and the D2H of areas / index / mask
-inside the timed region.  One JSON line is printed by rank 0.
+inside the timed region.  One JSON line is printed by rank 0; besides the contract keys it carries
+  roofline      tensor roofline of igemm_tc_kernel (+ `hbm_class`: the HBM-bound launches against the measured copy rate)
+  parity        engine vs the fp32 oracle on two full 562x744 frames of THIS run's weights, both storage types
+  dtype_ab      the other 16-bit storage type timed in the same process (the "same speed" claim)
+  selected_frame  the engine's selection checked against the fp32 oracle on its own top candidates
+  cpu_baseline / cpu_config0 / library_baseline   the oracle port on the host cores; BASELINE config[0] exactly; the stock
+                PyTorch eager -> cuDNN path on this same GPU (fp32 NCHW and bf16 channels-last, cudnn.benchmark=True)
 """
 import argparse
 import json
@@ -28,6 +35,7 @@ for p in (ROOT / "att-aspp-unet_b200", ROOT / "oracle"):
     sys.path.insert(0, str(p))
 
 H, W, N_FRAMES, BASE_C = 562, 744, 840, 32
+PEAK_FRAME = 304                   # SURVEY.md section 8d Config 2: the ellipse is largest at frame 304
 GFLOP_PER_FRAME = 160.319          # SURVEY.md section 8d / BASELINE.md section 3 (2*MAC, dense tap count)
 METRIC = "frames/sec Att-ASPP-UNet fwd (744x562 US)"
 
@@ -85,7 +93,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in out.splitlines():
             f = [t.strip() for t in line.split(",")]
             if len(f) < 8:
@@ -93,6 +101,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
@@ -100,29 +109,34 @@ class ClockSampler:
                     reasons.add(name)
         busy = [s for s in sm if s > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_median": statistics.median(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-WORKLOAD = ("config[1]: one 840-frame 744x562 uint8 sweep per GPU, AttentionASPPUNet base_c=32, BN-calibrated random weights, "
-            "forward + sigmoid/threshold/area + first-max argmax")
+WORKLOAD = ("config[1]: one 840-frame 744x562 uint8 sweep per GPU (840 distinct synthetic frames, ellipse largest at frame 304), "
+            "AttentionASPPUNet base_c=32, BN-calibrated random weights, forward + threshold/area + first-max argmax")
 
 
 def make_weights():
     import aau_oracle as O
     cfg = O.NetCfg(base_c=BASE_C)
-    g = torch.Generator().manual_seed(2025)
     calib = torch.from_numpy(O.synthetic_sweep(2, H // 2, W // 2, seed=7, peak=1).astype(np.float32) / 255.0).unsqueeze(1)
     sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), calib, cfg)
     return cfg, sd
 
 
-def make_sweep(n_unique=24, seed=2025):
-    """uint8 [840,562,744]: `n_unique` distinct synthetic frames tiled along the sweep with a per-frame intensity
-    ramp (generating 840 Rayleigh-speckle frames on the host would dominate the run; the network does the same work)."""
+def make_sweep(seed=2025, n_frames=N_FRAMES):
+    """SURVEY.md section 8d Config 2: uint8 [840,562,744], 840 DISTINCT frames -- fan-shaped field of view, Rayleigh speckle,
+    exact 0 outside, a bright ellipse whose axes vary smoothly with the frame index and peak at frame 304 (about 15 s of
+    host time; the generator is the oracle's, so every test and the CPU arms see the same kind of frame)."""
     import aau_oracle as O
-    base = O.synthetic_sweep(n_unique, H, W, seed=seed, peak=n_unique // 2)
-    reps = (N_FRAMES + n_unique - 1) // n_unique
-    return np.ascontiguousarray(np.concatenate([base] * reps)[:N_FRAMES])
+    return np.ascontiguousarray(O.synthetic_sweep(n_frames, H, W, seed=seed, peak=PEAK_FRAME))
+
+
+def host_threads(args):
+    """torchrun exports OMP_NUM_THREADS=1: a CPU arm must say how many threads it really uses, and use the host's."""
+    n = args.ref_threads if args.ref_threads > 0 else (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -133,11 +147,11 @@ def run_reference(args):
     if rank != 0:
         return
     import aau_oracle as O
+    threads = host_threads(args)
     cfg, sd = make_weights()
     frames = args.ref_frames
     vol = O.synthetic_sweep(frames, H, W, seed=2025, peak=frames // 2)
     x = torch.from_numpy(vol.astype(np.float32) / 255.0).unsqueeze(1)
-    threads = torch.get_num_threads()
 
     def step():
         logits = O.forward(sd, x, cfg)
@@ -152,11 +166,14 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     fps = frames * args.steps / dt
-    sample = f"{frames} synthetic 562x744 frames per step (one batch-{frames} fp32 forward + sigmoid + postprocess + select), of the 840-frame sweep"
+    sample = (f"bounded sample: {frames} synthetic 562x744 frames per step (one batch-{frames} fp32 forward + sigmoid + postprocess + select); "
+              f"frames/s extrapolates linearly to the 840-frame sweep (frames are independent)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames, "note": "bounded CPU sample of that workload"},
+            "config": {"workload": WORKLOAD, "frames_per_step": frames,
+                       "note": f"bounded {frames}-frame CPU sample of that workload, extrapolated; rank 0 only, {threads} host threads "
+                               f"whatever N (the host is shared by the N GPU ranks)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count(), "torch": torch.__version__},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -164,7 +181,7 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(cfg, sd, frames=8, reps=2):
+def cpu_baseline_sample(cfg, sd, threads, frames=8, reps=2):
     import aau_oracle as O
     vol = O.synthetic_sweep(frames, H, W, seed=2025, peak=frames // 2)
     x = torch.from_numpy(vol.astype(np.float32) / 255.0).unsqueeze(1)
@@ -174,9 +191,136 @@ def cpu_baseline_sample(cfg, sd, frames=8, reps=2):
         logits = O.forward(sd, x, cfg)
         O.select_fetal_abdomen_mask_and_frame(O.postprocess(torch.sigmoid(logits)[:, 0].numpy()))
     dt = time.perf_counter() - t0
-    return {"value": frames * reps / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": frames * reps / dt, "unit": "frames/s", "cores": threads, "kind": "port",
             "sample": f"{reps} x batch-{frames} of the sweep's 562x744 frames, fp32 torch CPU forward + numpy selection (oracle)",
             "host_cpus": os.cpu_count()}
+
+
+def cpu_config0(threads, reps=3):
+    """BASELINE.json configs[0] / SURVEY.md section 8d Config 1 exactly: AttentionASPPUNet(1,1,base_c=32) default init after
+    manual_seed(2025) (attention_aspp_unet_pipeline_stage.py:29,112), x = rand(1,1,512,512) seed 2025, fp32 CPU, no_grad."""
+    import aau_oracle as O
+    cfg = O.NetCfg(base_c=32)
+    sd = O.make_state_dict(cfg, 2025, "R0")
+    x = torch.rand(1, 1, 512, 512, generator=torch.Generator().manual_seed(2025))
+    O.forward(sd, x, cfg)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.forward(sd, x, cfg)
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    return {"config": "configs[0]: AttentionASPPUNet(base_c=32) fp32 forward, one 512x512 frame, CPU, default-init weights seed 2025",
+            "ms_per_forward": ms, "frames_per_s": 1e3 / ms, "cores": threads, "host_cpus": os.cpu_count(), "reps": reps, "kind": "port"}
+
+
+def parity_block(sd, cfg, dev, vol_np, frame_ids, dtypes, nets):
+    """Engine vs the fp32 CPU oracle on full 562x744 frames of this run's sweep and weights (north_star: logits within
+    2e-2 absolute, >= 99.9 % agreement of the thresholded masks)."""
+    import aau_oracle as O
+    from attention_aspp_unet import AttentionASPPUNet
+    x_u8 = np.ascontiguousarray(vol_np[frame_ids])
+    ref = O.forward(sd, torch.from_numpy(x_u8.astype(np.float32) / 255.0).unsqueeze(1), cfg)
+    out = {"frames": [int(i) for i in frame_ids], "shape": [len(frame_ids), H, W], "oracle": "oracle/aau_oracle.py fp32 CPU forward (pinned to the reference's own outputs, tests/golden)",
+           "logit_std": float(ref.std()), "bar": {"max_abs_err": 2e-2, "mask_agreement": 0.999}}
+    for dt in dtypes:
+        net = nets.get(dt)
+        if net is None:
+            net = AttentionASPPUNet(base_c=BASE_C, act_dtype=dt)
+            net.load_state_dict(sd, strict=True)
+            net.eval().prepare(dev)
+            nets[dt] = net
+        got = net(torch.from_numpy(x_u8).to(dev)).float().cpu()
+        err = (got - ref).abs()
+        agree = {str(t): float(((torch.sigmoid(got) > t) == (torch.sigmoid(ref) > t)).float().mean()) for t in (0.05, 0.48, 0.5)}
+        out[dt] = {"max_abs_err": float(err.max()), "mean_abs_err": float(err.mean()), "p999_abs_err": float(err.flatten().kthvalue(int(0.999 * err.numel())).values),
+                   "mask_agreement": agree, "meets_bar": bool(err.max() <= 2e-2 and min(agree.values()) >= 0.999)}
+    return out
+
+
+def selection_check(sd, cfg, vol_np, areas_np, best_idx, thr, k=4):
+    """The engine's selected frame against the fp32 oracle on the engine's own top-k candidates (a full-sweep CPU pass is
+    ~3 min): per-frame areas of both, the top-2 margin, and whether the margin exceeds the observed mask disagreement."""
+    import aau_oracle as O
+    order = np.argsort(-areas_np.astype(np.int64), kind="stable")[:k]
+    x = torch.from_numpy(vol_np[order].astype(np.float32) / 255.0).unsqueeze(1)
+    prob = torch.sigmoid(O.forward(sd, x, cfg))[:, 0].numpy()
+    ref_areas = O.frame_areas(prob, thr)
+    eng = [int(areas_np[i]) for i in order]
+    diff = int(np.abs(np.asarray(eng) - ref_areas.astype(np.int64)).max())
+    margin = int(eng[0] - eng[1]) if len(eng) > 1 else 0
+    ref_best = int(order[int(np.argmax(ref_areas))])
+    return {"candidates": [int(i) for i in order], "engine_areas": eng, "oracle_areas": [int(a) for a in ref_areas],
+            "max_area_diff": diff, "top2_margin": margin, "oracle_best_of_candidates": ref_best,
+            "index_parity": "exact" if ref_best == best_idx else ("within tie margin" if margin <= 2 * diff else "MISMATCH")}
+
+
+def library_baseline(sd, cfg, dev, vol_dev, thr, batches=(56, 8), reps=3):
+    """The reference's own GPU path on this same B200: stock PyTorch eager -> cuDNN with cudnn.benchmark=True
+    (attention_aspp_unet_pipeline_stage.py:553), the oracle's functional forward on CUDA tensors -- fp32 NCHW (what the
+    reference runs; TF32 off = torch's default for convolutions... see `tf32`) and bf16 channels-last autocast --
+    + torch.sigmoid / threshold / sum / argmax, CUDA-event timed over the sweep's own frames."""
+    import aau_oracle as O
+    out = {"what": "torch eager -> cuDNN (cudnn.benchmark=True), oracle/aau_oracle.py forward on CUDA tensors + sigmoid/threshold/sum/argmax",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "tf32_conv": bool(torch.backends.cudnn.allow_tf32), "rows": []}
+    bench_prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    sdc = {k: v.to(dev) for k, v in sd.items()}
+    try:
+        for B in batches:
+            xb = (vol_dev[:B].float() / 255.0).unsqueeze(1)
+            for mode in ("fp32_nchw", "bf16_channels_last"):
+                def fwd():
+                    if mode == "fp32_nchw":
+                        lg = O.forward(sdc, xb, cfg)
+                    else:
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            lg = O.forward(sdc, xb.contiguous(memory_format=torch.channels_last), cfg)
+                    areas = (torch.sigmoid(lg.float())[:, 0] > thr).sum((1, 2))
+                    return areas.argmax()
+                try:
+                    with torch.no_grad():
+                        for _ in range(2):
+                            fwd()
+                        torch.cuda.synchronize(dev)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(reps):
+                            fwd()
+                        e1.record()
+                        torch.cuda.synchronize(dev)
+                    ms = e0.elapsed_time(e1) / reps
+                    out["rows"].append({"mode": mode, "batch": B, "ms_per_forward": ms, "frames_per_s": 1e3 * B / ms,
+                                        "tflops": B * GFLOP_PER_FRAME / ms})
+                except Exception as ex:                                  # e.g. out of memory: report, never fail the bench
+                    out["rows"].append({"mode": mode, "batch": B, "error": str(ex)[:200]})
+                torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = bench_prev
+    return out
+
+
+def timed_device_sweeps(net, seg, vol_dev, logits_all, areas, best, B, thr, steps, warmup, dev, barrier, on_timed=None):
+    starts = list(range(0, N_FRAMES, B))
+
+    def device_step():
+        for s in starts:
+            b = min(B, N_FRAMES - s)
+            lg = net(vol_dev[s: s + b], out=logits_all[s: s + b])
+            seg._scores.run(lg[:, 0], 0, thr, areas[s: s + b], None, None)
+        seg._scores.best(areas, best)
+
+    for _ in range(warmup):
+        device_step()
+    net.check_device()
+    barrier()
+    if on_timed is not None:
+        on_timed()                                              # clock sampling starts with the timed region
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        device_step()
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1), len(starts)
 
 
 def run_engine(args):
@@ -204,18 +348,10 @@ def run_engine(args):
     vol_pinned = torch.from_numpy(vol_np).pin_memory()
     vol_dev = torch.from_numpy(vol_np).to(dev)
     B = args.batch
-    starts = list(range(0, N_FRAMES, B))
     logits_all = torch.empty((N_FRAMES, 1, H, W), dtype=torch.float32, device=dev)
     areas = torch.zeros(N_FRAMES, dtype=torch.int32, device=dev)
     best = torch.zeros(2, dtype=torch.int32, device=dev)
     thr = args.prob_thr
-
-    def device_step():
-        for s in starts:
-            b = min(B, N_FRAMES - s)
-            lg = net(vol_dev[s: s + b], out=logits_all[s: s + b])
-            seg._scores.run(lg[:, 0], 0, thr, areas[s: s + b], None, None)
-        seg._scores.best(areas, best)
 
     def barrier():
         if world > 1:
@@ -223,23 +359,13 @@ def run_engine(args):
         torch.cuda.synchronize(dev)
 
     # ---------------- kernel-only arm (inputs resident in HBM)
-    for _ in range(args.warmup):
-        device_step()
-    net.check_device()
     sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        device_step()
-    ev1.record()
-    barrier()
+    ms, n_batches = timed_device_sweeps(net, seg, vol_dev, logits_all, areas, best, B, thr, args.steps, args.warmup, dev, barrier,
+                                        on_timed=sampler.start if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    launches_per_step = len(starts) * (net.num_launches() + 1) + 1
+    launches_per_step = n_batches * (net.num_launches() + 1) + 1
     best_dev = [int(v) for v in best.cpu().numpy()]
+    areas_np = areas.cpu().numpy().copy()
 
     # ---------------- end-to-end arm (public API, pinned host input, results back on the host)
     res = None
@@ -257,11 +383,12 @@ def run_engine(args):
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))   # host work after the last kernel counts too
 
-    # ---------------- per-launch timing for the roofline (profile mode, one extra untimed sweep)
+    # ---------------- per-launch timing for the roofline (profile mode, extra untimed forwards)
     net.set_option("profile", 1)
     tc_ms = tc_fl = 0.0
     layer_rows = {}
     nb = 0
+    starts = list(range(0, N_FRAMES, B))
     for s in starts[: max(1, min(len(starts), 6))]:
         b = min(B, N_FRAMES - s)
         net(vol_dev[s: s + b], out=logits_all[s: s + b])
@@ -289,20 +416,37 @@ def run_engine(args):
     fps_e2e = frames_total / (ms_e2e / 1e3)
     tc_tflops = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     fwd_ms = sum(v["ms"] for v in layer_rows.values()) / max(nb, 1)
+    # the HBM-bound class: launches whose algorithmic bytes / HBM rate exceed their algorithmic FLOPs / tensor rate
+    hb_ms = hb_bytes = 0.0
+    hb_names = []
+    for name, v in layer_rows.items():
+        if v["bytes"] / (pk["hbm"] * 1e9) > v["flops"] / (pk["tc_sustained"] * 1e12) and v["ms"] > 0 and v["bytes"] > 0:
+            hb_ms += v["ms"]; hb_bytes += v["bytes"]; hb_names.append(name.split(" [")[0])
+    hbm_gbs = hb_bytes / (hb_ms / 1e3) / 1e9 if hb_ms > 0 else 0.0
     traffic, traffic_src = None, None
-    tp = ROOT / "profiles" / "r01_igemm_dram_traffic.json"          # ncu --set full capture of the igemm launches of one forward
-    if tp.exists():
-        try:
-            tj = json.loads(tp.read_text())
-            traffic = tj["dram_bytes_per_frame"] * B                 # per forward of this bench's batch, like `achieved`
-            traffic_src = f"ncu dram__bytes_read+write summed over the {tj['launches']} igemm launches of one forward: {tj['dram_bytes_per_frame'] / 1e6:.0f} MB per frame (profiles/r01_igemm_dram_traffic.json) x batch"
-        except Exception:
-            pass
+    for tp in (ROOT / "profiles" / "r02_dram_traffic_b56.json", ROOT / "profiles" / "r01_igemm_dram_traffic.json"):
+        if tp.exists():
+            try:
+                tj = json.loads(tp.read_text())
+                if int(tj.get("batch", 8)) == B:
+                    traffic = tj["dram_bytes_per_forward"]
+                    traffic_src = f"ncu dram__bytes_read+write summed over the {tj['launches']} igemm launches of ONE batch-{B} forward ({tp.name}): {traffic / B / 1e6:.0f} MB per frame"
+                else:
+                    traffic = tj["dram_bytes_per_frame"] * B
+                    traffic_src = f"EXTRAPOLATED from a batch-{tj.get('batch', 8)} ncu capture ({tp.name}: {tj['dram_bytes_per_frame'] / 1e6:.0f} MB per frame) x batch {B}"
+                break
+            except Exception:
+                pass
     roof = {"bound": "tensor", "achieved": tc_tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tc_tflops / pk["tc_sustained"],
-            "traffic": traffic, "traffic_note": traffic_src, "kernel": "igemm_tc_kernel", "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
+            "traffic": traffic, "traffic_note": traffic_src, "kernel": "igemm_tc_kernel", "peak_source": pk["source"] + " (sustained 16-bit dense: kernel timed inside a long step)",
+            "frac_of_burst_peak": tc_tflops / pk["tc_burst"],
             "note": f"algorithmic FLOPs of the {n_tc} igemm_tc_kernel launches of one forward / their summed CUDA-event time; "
                     f"they are {tc_ms / max(sum(v['ms'] for v in layer_rows.values()), 1e-9):.0%} of the forward",
-            "whole_forward_tflops": fps / world * GFLOP_PER_FRAME / 1e3, "whole_forward_frac": fps / world * GFLOP_PER_FRAME / 1e3 / pk["tc_sustained"]}
+            "whole_forward_tflops": fps / world * GFLOP_PER_FRAME / 1e3, "whole_forward_frac": fps / world * GFLOP_PER_FRAME / 1e3 / pk["tc_sustained"],
+            "whole_forward_frac_of_burst_peak": fps / world * GFLOP_PER_FRAME / 1e3 / pk["tc_burst"],
+            "hbm_class": {"bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm"],
+                          "share_of_forward": hb_ms / max(sum(v["ms"] for v in layer_rows.values()), 1e-9), "launches": hb_names,
+                          "note": "launches whose algorithmic bytes / measured copy rate exceed their FLOPs / tensor peak (stem, gates, transposed convs, full-resolution convs): summed algorithmic bytes / summed CUDA-event time"}}
     out_dir = ROOT / "gpurun_out"
     try:
         out_dir.mkdir(exist_ok=True)
@@ -315,16 +459,125 @@ def run_engine(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": WORKLOAD + (" (config[2]: one case per GPU, host gather)" if world > 1 else ""),
-                       "frames_per_step_per_gpu": N_FRAMES, "batch": B, "act_dtype": args.dtype, "l2": "inputs larger than L2 (351 MB sweep; >6 GB of activations per batch)",
+                       "frames_per_step_per_gpu": N_FRAMES, "batch": B, "act_dtype": args.dtype,
+                       "dtype_note": "16-bit storage (fp16 default: the 16-bit type that meets the 2e-2 / 99.9 % parity bar, see `parity`; same tcgen05 kind::f16 rate as bf16, see `dtype_ab`), fp32 accumulate",
+                       "l2": "inputs larger than L2 (351 MB sweep; >6 GB of activations per batch)",
                        "parallelism": f"dp{world} by case, no collective on the forward path"},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(res["h2d_bytes"]), "d2h_bytes_per_step": int(res["d2h_bytes"]),
                     "api": "FetalAbdomenSegmentation.segment_sweep(pinned uint8 sweep) -> areas, best index, post-processed mask"},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roof,
             "selected_frame": {"device_arm": best_dev[0], "e2e_arm": res["best_idx"], "area": res["best_area"], "prob_thr": thr,
-                               "distinct_areas": int(len(np.unique(areas.cpu().numpy())))}}
-    if world == 1:
-        line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, frames=args.cpu_frames, reps=5 if args.cpu_frames >= 8 else 2)   # ~10 s of CPU work by default
+                               "distinct_areas": int(len(np.unique(areas_np))), "ellipse_peak_frame": PEAK_FRAME}}
+    if world == 1 and not args.lean:
+        nets = {args.dtype: net}
+        other = "bf16" if args.dtype == "fp16" else "fp16"
+        try:                                                        # the other 16-bit storage type, same process, same sweep
+            net2 = AttentionASPPUNet(base_c=BASE_C, act_dtype=other)
+            net2.load_state_dict(sd, strict=True)
+            net2.eval().prepare(dev)
+            nets[other] = net2
+            seg2 = FetalAbdomenSegmentation(net=net2, batch=B, device=dev)
+            ms2, _ = timed_device_sweeps(net2, seg2, vol_dev, logits_all, areas, best, B, thr, max(1, min(args.steps, 2)), 1, dev, barrier)
+            line["dtype_ab"] = {args.dtype: fps, other: N_FRAMES * max(1, min(args.steps, 2)) / (ms2 / 1e3), "unit": "frames/s",
+                                "note": "device-resident arm, same process; the second type runs after the first, under the same power cap"}
+        except Exception as ex:
+            line["dtype_ab"] = {"error": str(ex)[:200]}
+        threads = host_threads(args)
+        try:
+            line["parity"] = parity_block(sd, cfg, dev, vol_np, [PEAK_FRAME, 17], [args.dtype, other], nets)
+        except Exception as ex:
+            line["parity"] = {"error": str(ex)[:200]}
+        try:
+            line["selected_frame"].update(selection_check(sd, cfg, vol_np, areas_np, best_dev[0], thr))
+        except Exception as ex:
+            line["selected_frame"]["oracle_check_error"] = str(ex)[:200]
+        nets.clear()
+        line["cpu_baseline"] = cpu_baseline_sample(cfg, sd, threads, frames=args.cpu_frames, reps=5 if args.cpu_frames >= 8 else 2)   # ~10 s of CPU work by default
+        line["cpu_config0"] = cpu_config0(threads)
+        if not args.no_library:
+            try:
+                line["library_baseline"] = library_baseline(sd, cfg, dev, vol_dev, thr)
+                for r in line["library_baseline"]["rows"]:
+                    if "frames_per_s" in r and r["batch"] == B:
+                        r["engine_over_library"] = fps / r["frames_per_s"]
+            except Exception as ex:
+                line["library_baseline"] = {"error": str(ex)[:200]}
     emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_split_sweep(args):
+    """ONE 840-frame sweep split into contiguous frame blocks over the N ranks (frames are
+    independent, model_attention_aspp.py:45-55): every rank runs segment_sweep(frame_range, finalize=False) from pinned host
+    memory, the per-frame areas are gathered (the only exchange), the global first-max index is taken and the OWNER rank
+    post-processes that one frame.  Reports time-to-answer (strong scaling: total work fixed as N grows)."""
+    import torch.distributed as dist
+    from attention_aspp_unet import AttentionASPPUNet
+    from fetal_abdomen import FetalAbdomenSegmentation, merge_shard_scores
+    from sharding import gather_areas, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, sd = make_weights()
+    net = AttentionASPPUNet(base_c=BASE_C, act_dtype=args.dtype)
+    net.load_state_dict(sd, strict=True)
+    net.eval().prepare(dev)
+    lo, hi = shard_range(N_FRAMES, world, rank)
+    n_local = hi - lo
+    # batch: the largest divisor-friendly size <= --batch that splits this rank's block evenly (105 frames -> 3 x 35, not 56 + 49)
+    nb = max(1, -(-n_local // args.batch))
+    B = -(-n_local // nb)
+    seg = FetalAbdomenSegmentation(net=net, batch=B, device=dev)
+    vol_np = make_sweep(seed=2025)                               # the same sweep on every rank (each uses its own block)
+    vol_pinned = torch.from_numpy(vol_np).pin_memory()
+    thr = args.prob_thr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def answer():
+        part = seg.segment_sweep(vol_pinned, frame_range=(lo, hi), prob_thr=thr, finalize=False)
+        all_areas = gather_areas(part["areas"], N_FRAMES, dev) if world > 1 else part["areas"]
+        areas, gidx = merge_shard_scores([all_areas])
+        mask = None
+        if gidx >= 0 and lo <= gidx < hi:                        # the owner finishes the selected frame from its resident logits
+            mask = seg._mask_from_logits(seg._logits_all[gidx - lo].reshape(1, H, W), thr)
+        return gidx, (int(areas[gidx]) if gidx >= 0 else 0), mask, part
+
+    for _ in range(max(1, args.warmup)):
+        answer()
+    barrier()
+    times = []
+    gidx = area = 0
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        gidx, area, mask, part = answer()
+        torch.cuda.synchronize(dev)
+        times.append(1e3 * (time.perf_counter() - t0))
+    t = torch.tensor([statistics.median(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        emit({"metric": "time-to-answer for ONE 840-frame 744x562 sweep split by contiguous frame blocks (strong scaling)", "value": ms, "unit": "ms",
+              "frames_per_s": N_FRAMES / (ms / 1e3), "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+              "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+              "config": {"workload": "config[2], frame-sharded: " + WORKLOAD, "frames_per_rank": n_local, "batch": B, "batches_per_rank": nb,
+                         "timing": "host wall clock around segment_sweep(pinned block) + gather_areas + owner's mask, median of steps, max over ranks",
+                         "parallelism": f"one sweep / {world} contiguous frame blocks; exchange = all-gather of int32 areas[840]"},
+              "e2e": {"value": N_FRAMES / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(part["h2d_bytes"]) * world,
+                      "d2h_bytes_per_step": 4 * N_FRAMES + H * W},
+              "selected_frame": {"index": int(gidx), "area": int(area)}, "gpu_launches": int(part["launches"]) * args.steps})
     if world > 1:
         dist.destroy_process_group()
 
@@ -335,11 +588,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--split", default="case", choices=["case", "sweep"], help="N>1: one sweep per GPU (weak scaling, default) or ONE sweep split by frame blocks")
     ap.add_argument("--batch", type=int, default=56, help="frames per forward (a divisor of 840)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"], help="16-bit storage type of activations / weights (fp32 accumulate)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (amode, resident, ctas)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="host threads of the CPU arms (0 = every host CPU; torchrun's OMP_NUM_THREADS=1 is overridden)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the cpu_baseline sample of the engine arm")
+    ap.add_argument("--lean", action="store_true", help="skip parity / dtype A/B / CPU and library baselines (A/B runs of the kernels)")
+    ap.add_argument("--no-library", action="store_true", help="skip the torch-eager / cuDNN baseline on the GPU")
     ap.add_argument("--prob-thr", type=float, default=0.5,
                     help="probability threshold of the per-frame area score (0.5 = the pipeline CLI's binarisation; the wrapper's "
                          "0.05 marks every pixel of a random-weight network, so every frame would tie at the full-frame area)")
@@ -351,7 +608,10 @@ def main():
     if not torch.cuda.is_available():
         emit({"error": "no CUDA device: the engine has no CPU fallback"})
         sys.exit(2)
-    run_engine(args)
+    if args.split == "sweep":
+        run_split_sweep(args)
+    else:
+        run_engine(args)
 
 
 if __name__ == "__main__":

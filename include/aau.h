@@ -36,7 +36,7 @@ typedef enum {
 enum { AAU_VARIANT_PIPELINE = 0, AAU_VARIANT_ABLATION = 1 };
 enum { AAU_ACT_BF16 = 0, AAU_ACT_FP16 = 1 };
 enum { AAU_X_F32 = 0, AAU_X_U8 = 1 };
-enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1, AAU_IN_U8 = 2 };
+enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1, AAU_IN_U8 = 2, AAU_IN_LOGIT_CUT = 3 };
 
 /* Constructor arguments.
  * Replaces AttentionASPPUNet.__init__(in_channels=1, num_classes=1, base_c=32)
@@ -94,8 +94,10 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
 
 /* Replaces the selection head: `torch.sigmoid(...)` (model_attention_aspp.py:54), `(prob > thr)` (:71),
  * `bin_.sum((1,2)).argmax()` (:74) and `select_fetal_abdomen_mask_and_frame` (:91-97).
- *   values : device float32 [N,H,W]: logits (AAU_IN_LOGITS; sigmoid is evaluated in fp32 on the device exactly as
- *            1/(1+exp(-x))), probabilities (AAU_IN_PROB, compared as they are), or a uint8 mask volume
+ *   values : device float32 [N,H,W]: logits (AAU_IN_LOGITS: `sigmoid(x) > prob_thr` is decided as `x > cut`, cut = the largest
+ *            fp32 whose correctly rounded fp32 sigmoid is <= prob_thr, found by bisection on the host -- no transcendental
+ *            per pixel, bit exact; AAU_IN_LOGIT_CUT: `prob_thr` already IS that cutoff in logit space, e.g. the one of the
+ *            caller's own sigmoid implementation), probabilities (AAU_IN_PROB, compared as they are), or a uint8 mask volume
  *            (AAU_IN_U8: `areas` receives the per-frame sum of byte values as `mask_3d.sum((1,2))` does, and
  *            `mask` receives `v > 0`; prob_thr is ignored);
  *   prob_thr: threshold on the probability (0.05 in the reference)

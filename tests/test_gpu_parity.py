@@ -1,11 +1,12 @@
 """GPU parity tests (-m gpu): the CUDA path through libaau.so against the CPU oracle on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): logits within 2e-2 absolute of the fp32 reference and >= 99.9 % agreement on
-thresholded masks for the literal "random-init weights" regime (R0); frame index and integer post-processing bit exact
-given identical masks.  Regime R1 (BN-calibrated random weights, SURVEY.md section 7 hard part 1) makes a random
-BN+ReLU network chaotic (a single bf16 rounding of the INPUT already moves the fp32 reference's logits by ~5e-3 mean /
-4e-2 max), so there the bar is stated relative to what 16-bit storage can give: the engine must be at least as close to
-the fp32 reference as stock PyTorch bf16 autocast on the same GPU, and the fp16-storage mode must be ~8x closer still.
+thresholded masks; frame index and integer post-processing bit exact given identical masks.  The literal bar is asserted
+in BOTH weight regimes for the headline storage type (fp16: `test_r0_literal_bar`, `test_r1_literal_bar_headline_dtype`
+-- the benchmarked configuration: 562x744, c=32, BN-calibrated R1 weights, thresholds 0.05 / 0.48 / 0.5).  bf16 storage
+cannot meet it in R1 (a random BN+ReLU network is chaotic: a single bf16 rounding of the INPUT already moves the fp32
+reference's logits by ~5e-3 mean / 4e-2 max), so for that optional mode the bar is relative: at least as close to the
+fp32 reference as stock PyTorch bf16 autocast on the same GPU, with fp16 ~8x closer still.
 """
 import numpy as np
 import pytest
@@ -17,7 +18,7 @@ from conftest import GOLDEN, golden_case
 pytestmark = pytest.mark.gpu
 
 
-def make_net(cfg, sd, dtype="bf16"):
+def make_net(cfg, sd, dtype="fp16"):
     from attention_aspp_unet import AttentionASPPUNet
     kw = dict(base_c=cfg.base_c, act_dtype=dtype)
     if cfg.variant == "ablation":
@@ -48,13 +49,14 @@ def autocast_error(sd, x, cfg, ref):
 
 
 # ------------------------------------------------------------------------------------------------ regime R0
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("c,shape", [(32, (2, 128, 160)), (16, (8, 224, 224)), (32, (1, 562, 744))])
-def test_r0_literal_bar(c, shape):
+def test_r0_literal_bar(c, shape, dtype):
     cfg = O.NetCfg(base_c=c)
     sd = O.make_state_dict(cfg, 2025, "R0")
     x = torch.rand(*shape[:1], 1, *shape[1:], generator=torch.Generator().manual_seed(2025))
     ref = O.forward(sd, x, cfg)
-    net = make_net(cfg, sd)
+    net = make_net(cfg, sd, dtype)
     out = net(x.cuda()).cpu()
     net.check_device()
     assert (out - ref).abs().max().item() <= 2e-2                     # north_star: logits within 2e-2 (bf16)
@@ -63,6 +65,30 @@ def test_r0_literal_bar(c, shape):
 
 
 # ------------------------------------------------------------------------------------------------ regime R1
+@pytest.mark.parametrize("inp", ["sweep_u8", "rand_f32"])
+def test_r1_literal_bar_headline_dtype(inp):
+    """The benchmarked configuration -- one full 562x744 frame, c=32, BN-calibrated R1 weights, fp16 storage -- against
+    the LITERAL north-star bar at every threshold the reference uses (0.05 wrapper, 0.48 CLI, 0.5 bench)."""
+    cfg = O.NetCfg(base_c=32)
+    if inp == "sweep_u8":                                             # bench.py's weights and frame type (uint8 -> tensor-core stem)
+        calib = torch.from_numpy(O.synthetic_sweep(2, 281, 372, seed=7, peak=1).astype(np.float32) / 255.0).unsqueeze(1)
+        sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), calib, cfg)
+        vol = O.synthetic_sweep(1, 562, 744, seed=31, peak=0)
+        x, xin = torch.from_numpy(vol.astype(np.float32) / 255.0).unsqueeze(1), torch.from_numpy(vol)
+    else:                                                              # float frames in [0,1] (the module contract; FMA stem)
+        sd, x = r1_case(cfg, (1, 562, 744))
+        xin = x
+    ref = O.forward(sd, x, cfg)
+    net = make_net(cfg, sd, "fp16")
+    out = net(xin.cuda()).cpu()
+    net.check_device()
+    err = (out - ref).abs()
+    agree = {t: agreement(out, ref, t) for t in (0.05, 0.48, 0.5)}
+    print(f"\n[R1 literal bar, fp16, {inp}] max|err| {err.max():.5f} mean {err.mean():.6f} (logit std {ref.std():.3f}); agreement {agree}")
+    assert err.max().item() <= 2e-2                                  # north_star: logits within 2e-2 absolute
+    assert min(agree.values()) >= 0.999                              # north_star: >= 99.9 % pixel agreement on thresholded masks
+
+
 @pytest.mark.parametrize("c,shape", [(32, (2, 141, 93)), (16, (2, 80, 72)), (48, (1, 64, 80)), (32, (1, 562, 744))])
 def test_r1_as_close_as_library_bf16_and_fp16_much_closer(c, shape):
     cfg = O.NetCfg(base_c=c)
@@ -91,7 +117,7 @@ def test_golden_fixture_full_frame(manifest):
     out = make_net(cfg, sd, "fp16")(x.cuda()).cpu().numpy()[:, :, ::s, ::s]
     d = np.abs(out - gold["logits"])
     print(f"\n[golden 562x744 fp16] max {d.max():.4f} mean {d.mean():.5f}")
-    assert d.mean() < 0.01 and d.max() < 0.1
+    assert d.mean() < 2e-3 and d.max() <= 2e-2                       # the literal north-star bar against the REAL reference's output
 
 
 @pytest.mark.parametrize("name", ["abl_full_c16_R1_80x72", "abl_noatt_c16_R1_80x72", "abl_noaspp_c16_R1_80x72",
@@ -111,7 +137,7 @@ def test_golden_fixtures_variants(name, manifest):
             assert tuple(got.shape) == want.shape                      # disabled gates: zeros(1,1,1,1)
             assert np.abs(got.cpu().numpy() - want).max() < 5e-3       # psi in [0,1]
     d = np.abs(logits.cpu().numpy() - gold["logits"])
-    assert d.mean() < 5e-3 and d.max() < 5e-2, (name, d.mean(), d.max())
+    assert d.mean() < 2e-3 and d.max() <= 2e-2, (name, d.mean(), d.max())   # literal bar, real reference outputs
 
 
 def test_layer_by_layer_fp16():
@@ -130,11 +156,12 @@ def test_layer_by_layer_fp16():
 
 
 # ------------------------------------------------------------------------------------------------ properties at full size
-def test_full_size_invariants():
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_full_size_invariants(dtype):
     cfg = O.NetCfg(base_c=32)
     sd = O.calibrate_bn(O.make_state_dict(cfg, 2025, "R1"), torch.rand(2, 1, 96, 96, generator=torch.Generator().manual_seed(1)), cfg)
     vol = O.synthetic_sweep(5, 562, 744, seed=4, peak=2)
-    net = make_net(cfg, sd)
+    net = make_net(cfg, sd, dtype)
     xu8 = torch.from_numpy(vol).cuda()
     a = net(xu8)
     b = net(xu8)
@@ -231,10 +258,25 @@ def test_frame_scores_bit_exact():
             mask = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
             seg._scores.run(logits.cuda(), 0, thr, areas, best, mask)
             got = areas.cpu().numpy()
-            # device expf vs the CPU's sigmoid may differ by one ulp exactly at the threshold: allow 1e-5 of the pixels
-            assert np.abs(got - want).max() <= max(1, int(1e-5 * h * w)), (n, h, w, thr)
+            # the threshold is applied in logit space with the cutoff of the host's own torch.sigmoid (fetal_abdomen.
+            # logit_cutoff): no transcendental on the device, no allowance
+            assert np.array_equal(got, want), (n, h, w, thr, np.abs(got - want).max())
             assert int(best[0]) == int(got.argmax()) and int(best[1]) == int(got.max())
             assert np.array_equal(mask.cpu().numpy().sum((1, 2)), got)
+    # the C ABI's own AAU_IN_LOGITS path (cutoff of a correctly rounded fp32 sigmoid, found inside the library) agrees with the
+    # host-calibrated one: at most a pixel whose logit sits within an ulp of the cutoff may differ
+    import ctypes as C
+    import _capi
+    logits = torch.from_numpy(rng.normal(0, 3, (3, 200, 300)).astype(np.float32)).cuda()
+    for thr in (0.05, 0.48, 0.5):
+        a0 = torch.zeros(3, dtype=torch.int32, device="cuda")
+        a3 = torch.zeros(3, dtype=torch.int32, device="cuda")
+        st = _capi.lib().aau_frame_scores(seg.net.engine_handle(), logits.data_ptr(), _capi.AAU_IN_LOGITS, 3, 200, 300, C.c_float(thr),
+                                          a0.data_ptr(), None, None, None)
+        assert st == 0
+        seg._scores.run(logits, _capi.AAU_IN_LOGITS, thr, a3, None, None)
+        torch.cuda.synchronize()
+        assert (a0 - a3).abs().max().item() <= 1
     m2, idx = select_fetal_abdomen_mask_and_frame(np.array([[0, 9], [0, 0]], np.uint8))
     assert idx == 0 and m2.tolist() == [[0, 1], [0, 0]]
     big = np.zeros((4, 8, 8), np.uint8)
@@ -333,7 +375,8 @@ def test_fused_transposed_conv_and_bilinear_fixup(c, shape):
 
 # ------------------------------------------------------------------------------------------------ small / odd shapes
 @pytest.mark.parametrize("c,shape", [(16, (1, 16, 16)), (16, (2, 17, 33)), (16, (1, 31, 64)), (16, (3, 48, 50)), (16, (1, 95, 161)),
-                                     (16, (2, 64, 36)), (32, (1, 33, 47)), (32, (5, 18, 130))])
+                                     (16, (2, 64, 36)), (32, (1, 33, 47)), (32, (5, 18, 130)),
+                                     (64, (1, 48, 64)), (80, (2, 33, 47))])   # c = 80: 8c = 640 channels = 320 channel pairs > 256 threads in the ASPP pooling sum
 def test_small_and_odd_shapes(c, shape):
     """Planner corner cases: frames smaller than a tile, widths below one row-shifted tile, odd sizes at every level."""
     cfg = O.NetCfg(base_c=c)

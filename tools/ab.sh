@@ -5,8 +5,8 @@ for i in $(seq 1 $R); do
   for V in A B; do
     O="$A"; [ $V = B ] && O="$B"
     E="${O%%;*}"; [ "$E" = "$O" ] && E=""; O="${O#*;}"       # "ENV=val ...;bench options" (the env part is optional)
-    env $E python bench.py --steps 2 --warmup 2 --cpu-frames 1 --batch 28 $O > gpurun_out/ab_$V$i.json 2> gpurun_out/ab_$V$i.err
-    cp gpurun_out/layers_b28_bf16.json gpurun_out/ab_layers_$V$i.json
+    env $E python bench.py --steps 2 --warmup 2 --lean --batch ${AB_BATCH:-56} $O > gpurun_out/ab_$V$i.json 2> gpurun_out/ab_$V$i.err
+    cp gpurun_out/layers_b${AB_BATCH:-56}_${AB_DTYPE:-fp16}.json gpurun_out/ab_layers_$V$i.json
   done
 done
 python - "$R" <<'PY'
