@@ -667,4 +667,117 @@ __global__ void __launch_bounds__(256) tta_prob_kernel(const float* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-slice head and tail of the pipeline CLI around the network (attention_aspp_unet_pipeline_stage.py:492-498,
+// test_ablation.py:826-834): `Resize(512, 512)` of the conditioned uint8 frame before it, and after it
+//   prob = cv2.resize(prob, (W, H)); prob = cv2.GaussianBlur(prob, (5, 5), 0); mask = (prob > THR)
+// -- so that only uint8 masks (and their areas) ever leave the device.
+//
+// resize_u8_linear_kernel reproduces cv2.resize(uint8, INTER_LINEAR) BIT-EXACTLY (OpenCV's fixed-point scheme, checked
+// against cv2 4.13 for up- and down-scaling in tests/test_host_cpu.py through its numpy twin): per axis
+//   f = float((d + 0.5) * (1 / (dst / src)) - 0.5), s = floor(f), f -= s,   coefficients round(f * 2048), round((1 - f) * 2048)
+// columns: s < 0 or s >= src - 1 reset f to 0 (and clamp s); rows: no reset, the two source rows are clamped instead;
+// horizontal pass in int32 (scale 2^11), vertical pass ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2.
+__device__ __forceinline__ void cv_linear_coef(int d, double scale, int src, bool reset, int& s, float& f) {
+    const float ff = (float)(((double)d + 0.5) * scale - 0.5);
+    s = (int)floorf(ff);
+    f = ff - (float)s;
+    if (reset) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+    }
+}
+__global__ void __launch_bounds__(256) resize_u8_linear_kernel(const uint8_t* __restrict__ src, int SH, int SW, uint8_t* __restrict__ dst, int DH, int DW,
+                                                               double scale_x, double scale_y) {
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (dx >= DW || dy >= DH) return;
+    const uint8_t* img = src + (size_t)blockIdx.z * SH * SW;
+    int sx, sy;
+    float fx, fy;
+    cv_linear_coef(dx, scale_x, SW, true, sx, fx);
+    cv_linear_coef(dy, scale_y, SH, false, sy, fy);
+    const int a1 = __float2int_rn(fx * 2048.f), a0 = __float2int_rn((1.f - fx) * 2048.f);
+    const int b1 = __float2int_rn(fy * 2048.f), b0 = __float2int_rn((1.f - fy) * 2048.f);
+    const int x1 = min(sx + 1, SW - 1), y0 = min(max(sy, 0), SH - 1), y1 = min(max(sy + 1, 0), SH - 1);
+    const int h0 = (int)__ldg(img + (size_t)y0 * SW + sx) * a0 + (int)__ldg(img + (size_t)y0 * SW + x1) * a1;
+    const int h1 = (int)__ldg(img + (size_t)y1 * SW + sx) * a0 + (int)__ldg(img + (size_t)y1 * SW + x1) * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    dst[((size_t)blockIdx.z * DH + dy) * DW + dx] = (uint8_t)min(max(v, 0), 255);
+}
+
+// tail_mask_kernel: one 32x32 output tile per block.  The (32+4)^2 bilinear samples the 5x5 blur of the tile needs are
+// formed once in shared memory (cv2.resize float32 INTER_LINEAR: coefficients from the double-precision source coordinate,
+// same clamping rules as above; borders of the blur are BORDER_REFLECT_101), then the separable [1 4 6 4 1] / 16 kernel
+// (what cv2.GaussianBlur uses for ksize 5, sigma 0) runs as a row pass and a column pass in fp32, the result is compared
+// with THR, written as uint8 {0,1} and counted (warp shuffles + one integer atomic per block).  OpenCV's own summation
+// order differs in the last bit (vectorised FMA paths), so parity here is a tolerance, not bit equality: probabilities
+// within 1e-6, masks identical except where a blurred probability sits within that distance of THR.
+enum { TAIL_T = 32, TAIL_R = TAIL_T + 4 };
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+__global__ void __launch_bounds__(256) tail_mask_kernel(const float* __restrict__ prob, int PH, int PW, int H, int W, double scale_x, double scale_y,
+                                                        float thr, uint8_t* __restrict__ mask, int* __restrict__ areas) {
+    __shared__ float s_r[TAIL_R][TAIL_R + 1];
+    __shared__ float s_t[TAIL_R][TAIL_T + 1];
+    __shared__ int s_x0[TAIL_R], s_y0[TAIL_R];
+    __shared__ float s_fx[TAIL_R], s_fy[TAIL_R];
+    __shared__ int s_cnt[8];
+    const int frame = blockIdx.z, x0 = blockIdx.x * TAIL_T, y0 = blockIdx.y * TAIL_T;
+    const float* src = prob + (size_t)frame * PH * PW;
+    if (threadIdx.x < 2 * TAIL_R) {                                  // source index / weight of every row and column of the halo tile
+        const bool is_y = threadIdx.x >= TAIL_R;
+        const int k = is_y ? threadIdx.x - TAIL_R : threadIdx.x;
+        const int d = reflect101((is_y ? y0 : x0) - 2 + k, is_y ? H : W);
+        const double c = ((double)d + 0.5) * (is_y ? scale_y : scale_x) - 0.5;
+        int sidx = (int)floor(c);
+        float f = (float)(c - (double)sidx);
+        if (!is_y) {
+            if (sidx < 0) { sidx = 0; f = 0.f; }
+            if (sidx >= PW - 1) { sidx = PW - 1; f = 0.f; }
+            s_x0[k] = sidx; s_fx[k] = f;
+        } else {
+            s_y0[k] = sidx; s_fy[k] = f;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TAIL_R * TAIL_R; i += 256) {
+        const int r = i / TAIL_R, c = i - r * TAIL_R;
+        const int sx = s_x0[c], sx1 = min(sx + 1, PW - 1);
+        const int sy = s_y0[r], ya = min(max(sy, 0), PH - 1), yb = min(max(sy + 1, 0), PH - 1);
+        const float fx = s_fx[c], fy = s_fy[r];
+        const float h0 = __fadd_rn(__fmul_rn(__ldg(src + (size_t)ya * PW + sx), 1.f - fx), __fmul_rn(__ldg(src + (size_t)ya * PW + sx1), fx));
+        const float h1 = __fadd_rn(__fmul_rn(__ldg(src + (size_t)yb * PW + sx), 1.f - fx), __fmul_rn(__ldg(src + (size_t)yb * PW + sx1), fx));
+        s_r[r][c] = __fadd_rn(__fmul_rn(h0, 1.f - fy), __fmul_rn(h1, fy));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TAIL_R * TAIL_T; i += 256) {       // row pass
+        const int r = i / TAIL_T, c = i - r * TAIL_T;
+        s_t[r][c] = 0.0625f * (s_r[r][c] + s_r[r][c + 4]) + 0.25f * (s_r[r][c + 1] + s_r[r][c + 3]) + 0.375f * s_r[r][c + 2];
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < TAIL_T * TAIL_T; i += 256) {       // column pass, threshold, count
+        const int r = i / TAIL_T, c = i - r * TAIL_T;
+        const int y = y0 + r, x = x0 + c;
+        if (y < H && x < W) {
+            const float v = 0.0625f * (s_t[r][c] + s_t[r + 4][c]) + 0.25f * (s_t[r + 1][c] + s_t[r + 3][c]) + 0.375f * s_t[r + 2][c];
+            const int b = v > thr;
+            cnt += b;
+            mask[((size_t)frame * H + y) * W + x] = (uint8_t)b;
+        }
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < 8 ? s_cnt[threadIdx.x] : 0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && v) atomicAdd(areas + frame, v);
+    }
+}
+
 }  // namespace aau

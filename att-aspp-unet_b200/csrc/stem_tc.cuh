@@ -1,7 +1,9 @@
 // d1.0 on the tensor cores: Conv2d(1 -> C, 3x3, pad 1) + BN + ReLU of a uint8 sweep as an implicit GEMM whose K = 9
 // taps are padded to one K = 16 tcgen05.mma per 128 pixels (reference: attention_aspp_unet_pipeline_stage.py:24-33,
 // d1 = DoubleConv(1, c); the frame is divided by 255 before it -- here 1/255 is folded into the weights, so the A
-// operand holds the raw pixel values 0..255, which bf16 / fp16 represent exactly).
+// operand holds the raw pixel values 0..255, which bf16 / fp16 represent exactly; the weights go in as two 16-bit terms,
+// hi + lo, one MMA each into the same accumulator, so the layer computes with ~22-bit weights: as the FIRST layer its
+// weight rounding was the largest single source of logit error of the whole 16-bit network).
 //
 // Why not FMAs: 288 FMAs per pixel put the packed-fp32 stem at 2.9 TB/s of output (profiles/r01_ncu_v10_stem.txt, FMA
 // pipe bound); on the tensor pipe the same work is one 40-cycle MMA per 128 pixels and the layer is bounded by writing
@@ -30,7 +32,7 @@ enum { ERR_STEM_BUILD_WAIT = 111, ERR_STEM_MMA_WAIT = 112, ERR_STEM_EPI_WAIT = 1
 struct StemTcParams {
     CUtensorMap tmC;        // (C, P) 16-bit output, box (CB, 128), swizzle CB*2 bytes
     const uint8_t* x;       // [P] pixels, frames contiguous
-    const uint16_t* wB;     // [C][16] K-major weights w*s/255 in the activation type (taps 0..8, then zeros)
+    const uint16_t* wB;     // [2][C][16] K-major weights w*s/255 as hi + lo terms in the activation type (taps 0..8, then zeros)
     const float* bias;      // [C]
     int* err;
     uint32_t P;             // B*H*W
@@ -43,7 +45,7 @@ struct StemTcParams {
 };
 
 static inline size_t stem_tc_smem_bytes(int C) {
-    return 1024 /*align*/ + 2 * STEM_TC_SUB * 4096 /*A*/ + 2048 /*B*/ + 2 * STEM_TC_SUB * 128 * C * 2 /*staging*/ + STEM_IN_SLOTS * STEM_IN_SLOT_BYTES /*input ring*/;
+    return 1024 /*align*/ + 2 * STEM_TC_SUB * 4096 /*A*/ + 4096 /*B hi, lo*/ + 2 * STEM_TC_SUB * 128 * C * 2 /*staging*/ + STEM_IN_SLOTS * STEM_IN_SLOT_BYTES /*input ring*/;
 }
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem0;                                      // [stage][sub][128 rows][32 B], 32-byte swizzle
     const uint32_t smem_b = smem_a + 2 * STEM_TC_SUB * 4096;            // [C rows][32 B], same swizzle
-    const uint32_t smem_c = smem_b + 2048;                              // [group][sub][chunk][128 rows][CB*2 B]
+    const uint32_t smem_c = smem_b + 4096;                              // [group][sub][chunk][128 rows][CB*2 B]
     const int C = P.C;
     const uint32_t smem_in = smem_c + (uint32_t)(2 * STEM_TC_SUB * 128 * C * 2);   // [slot][row -1, 0, +1][544 B]
     // a macro-tile is "fast" when its three row segments, widened to 16-byte alignment, lie inside the pixel buffer
@@ -88,10 +90,12 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
         ptx::tmem_alloc(&tmem_base_smem, (uint32_t)P.tmem_cols);
         ptx::tmem_relinquish();
         // weights: C rows of 16 K-values (32 bytes), rows swizzled exactly as TMA would have written them
-        for (int i = lane; i < C * 2; i += 32) {
-            const int n = i >> 1, c = i & 1;
+        // (two matrices: the high-order terms at smem_b, the low-order terms 2 KB behind)
+        for (int i = lane; i < C * 4; i += 32) {
+            const int part = i >= C * 2 ? 1 : 0, k = i - part * C * 2;
+            const int n = k >> 1, c = k & 1;
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.wB) + i);
-            sts128(smem_b + (uint32_t)(n * 32 + ((c ^ ((n >> 2) & 1)) << 4)), v);
+            sts128(smem_b + (uint32_t)(part * 2048 + n * 32 + ((c ^ ((n >> 2) & 1)) << 4)), v);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
     if (warp == 0) {
         // =========================== MMA issuer ===========================
         const uint32_t idesc = ptx::make_idesc_f16(128, C, F16);
-        const uint64_t b_desc = ptx::make_kmajor_desc(smem_b, 32);
+        const uint64_t b_desc = ptx::make_kmajor_desc(smem_b, 32), b_lo_desc = ptx::make_kmajor_desc(smem_b + 2048, 32);
         int i = 0;
         for (int m = blockIdx.x; m < P.n_macro; m += gridDim.x, ++i) {
             const int s = i & 1;
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 2) stem_tc_kernel(const __gri
                 for (int j = 0; j < STEM_TC_SUB; ++j) {
                     const uint64_t a_desc = ptx::make_kmajor_desc(smem_a + (uint32_t)((s * STEM_TC_SUB + j) * 4096), 32);
                     ptx::umma_f16(tmem_base + (uint32_t)((s * STEM_TC_SUB + j) * C), a_desc, b_desc, idesc, 0u);
+                    ptx::umma_f16(tmem_base + (uint32_t)((s * STEM_TC_SUB + j) * C), a_desc, b_lo_desc, idesc, 1u);   // + pixels x low-order weight terms
                 }
                 ptx::umma_commit(&a_empty[s]);
                 ptx::umma_commit(&t_full[s]);

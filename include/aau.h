@@ -123,6 +123,18 @@ int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void
 int aau_flip_w(aau_handle* h, const void* x, int x_dtype, int64_t rows, int W, void* y, void* stream);
 int aau_tta_prob(aau_handle* h, const float* logits, const float* logits_of_flipped, int64_t rows, int W, float* prob, void* stream);
 
+/* Per-slice head and tail of the pipeline CLI's slice loop around the network (attention_aspp_unet_pipeline_stage.py:492-498,
+ * test_ablation.py:826-834).
+ * aau_resize_u8 replaces `Resize(IMG_SIZE, IMG_SIZE)` = cv2.resize(uint8, INTER_LINEAR) of the conditioned frame, bit exact
+ *   with OpenCV's fixed-point scheme:  src device uint8 [N,SH,SW] -> dst device uint8 [N,DH,DW] (not in place).
+ * aau_tail_masks replaces `cv2.resize(prob, (W, H))`, `cv2.GaussianBlur(prob, (5, 5), 0)` and `(prob > THR)`:
+ *   prob device float32 [N,PH,PW] (the TTA probabilities) -> mask device uint8 [N,H,W] in {0,1}, areas device int32 [N]
+ *   (overwritten) = pixels set per frame.  fp32 arithmetic; equal to OpenCV's up to its last-bit summation order.
+ * Asynchronous on `stream`. */
+int aau_resize_u8(aau_handle* h, const uint8_t* src, int N, int SH, int SW, uint8_t* dst, int DH, int DW, void* stream);
+int aau_tail_masks(aau_handle* h, const float* prob, int N, int PH, int PW, int H, int W, float thr, uint8_t* mask,
+                   int32_t* areas, void* stream);
+
 /* Frame conditioning of the reference wrapper on the device, bit exact with the OpenCV calls it makes
  * (model_attention_aspp.py:11-17, inference.py:147-190): per frame `cv2.normalize(NORM_MINMAX, 0, 255)` -> uint8,
  * `cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8,8)).apply`, `cv2.medianBlur(3)`.
@@ -160,6 +172,9 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *   "tb"       1/0 per-tap staged tiles of small images may span two frames
  *   "spec"     1/0 use the kernel instantiations specialised per (staging mode, epilogue, K step, fused pool)
  *   "stem_tc"  1/0 uint8 frames run d1.0 on the tensor cores (0: packed-fp32 stem, as float frames always do)
+ *   "stem_lo"  1/0 the tensor-core stem carries its weights as two 16-bit terms (hi + lo, two MMAs): ~22-bit first-layer weights
+ *   "keep_sum" 1/0 3x3 weights are rounded to 16 bits with the rule that preserves every (out, in) window's tap sum
+ *              (both re-run the weight preparation: they synchronise the device)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
  *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
  *   "profile"  0/1 record CUDA events around every launch of the following forwards (aau_op_profile). */

@@ -78,8 +78,27 @@ def test_engine_tta_and_case_prediction(gold, case, tmp_path):
     assert (got - ref).abs().max().item() < 2e-3
     flipped = pp.predict_prob_tta(torch.flip(x, [-1]).cuda()).cpu()
     assert (torch.flip(flipped, [-1]) - got).abs().max().item() < 1e-3          # TTA output is flip-equivariant
-    # whole recipe on the sweep: blurred probabilities, refined masks, best frame, AC
+    # device head / tail of the slice loop against the OpenCV calls they replace
     import cv2
+    rng = np.random.default_rng(3)
+    for (sh, sw, dh, dw) in ((281, 372, 512, 512), (562, 744, 512, 512), (97, 131, 512, 512), (600, 800, 512, 512), (512, 512, 300, 200)):
+        img = rng.integers(0, 256, (2, sh, sw), dtype=np.uint8)
+        got = pp.resize_on_device(torch.from_numpy(img).cuda(), (dh, dw)).cpu().numpy()
+        want = np.stack([cv2.resize(f, (dw, dh), interpolation=cv2.INTER_LINEAR) for f in img])
+        assert np.array_equal(got, want), (sh, sw, dh, dw)           # cv2.resize(uint8, INTER_LINEAR): bit exact
+    for (H, W) in ((281, 372), (562, 744), (97, 131), (33, 31)):
+        prob = torch.sigmoid(torch.from_numpy(rng.normal(0, 2, (3, 64, 64)).astype(np.float32)))
+        prob = torch.nn.functional.interpolate(prob[None], size=(512, 512), mode="bicubic", align_corners=False)[0].clamp(0, 1).contiguous()
+        m, a = pp.tail_on_device(prob.cuda(), (H, W), c["thr"])
+        blurred = np.stack([cv2.GaussianBlur(cv2.resize(p_, (W, H)), (5, 5), 0) for p_ in prob.numpy()])
+        want = (blurred > c["thr"]).astype(np.uint8)
+        near = np.abs(blurred - c["thr"]) < 2e-6                     # OpenCV's own last-bit summation order decides these
+        assert np.array_equal(m.cpu().numpy()[~near], want[~near]) and near.mean() < 1e-4, (H, W)
+        assert np.array_equal(a.cpu().numpy(), m.cpu().numpy().reshape(3, -1).sum(1))
+    # whole recipe on the sweep: blurred probabilities, refined masks, best frame, AC
+    raw, raw_areas = pp.raw_masks(sweep, c["thr"])
+    gold_raw = unpack(gold["raw_masks"], c)
+    assert (raw == gold_raw).mean() >= 0.998 and np.array_equal(raw_areas, raw.reshape(len(raw), -1).sum(1))
     masks = pp.predict_masks(sweep, c["thr"])
     refined = unpack(gold["refined"], c)
     assert masks.shape == refined.shape and masks.dtype == np.uint8
