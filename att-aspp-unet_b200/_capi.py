@@ -47,6 +47,7 @@ SYMBOLS = [
     ("aau_frame_scores", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aau_best_frame", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("aau_best_frame_mask", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aau_sigmoid", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("aau_flip_w", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     ("aau_tta_prob", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
@@ -57,6 +58,7 @@ SYMBOLS = [
     ("aau_device_fault", C.c_int, [C.c_void_p]),
     ("aau_num_launches", C.c_int, [C.c_void_p]),
     ("aau_num_ops", C.c_int, [C.c_void_p]),
+    ("aau_last_forward_was_graph", C.c_int, [C.c_void_p]),
     ("aau_op_profile", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("aau_debug_tensor", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_int)] * 6),

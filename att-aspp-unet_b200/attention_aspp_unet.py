@@ -157,8 +157,9 @@ class AttentionASPPUNet(nn.Module):
             raise ValueError("use_att / use_aspp / att_depth belong to the ablation twin")
         if in_channels != 1 or num_classes != 1:
             raise ValueError("the B200 engine implements the reference's only configuration: in_channels=1, num_classes=1")
-        if base_c < 16 or base_c % 16:
-            raise ValueError("base_c must be a multiple of 16 (the reference uses 16, 32 and 48)")
+        if base_c < 16 or base_c % 16 or base_c > 64:
+            raise ValueError("base_c must be 16, 32, 48 or 64 (the reference uses 16, 32 and 48): the fused gate epilogue holds all "
+                             "F_int = 4 * base_c channels of the deepest gate in one 256-column accumulator tile")
         if act_dtype not in ("bf16", "fp16"):
             raise ValueError("act_dtype must be 'bf16' or 'fp16'")
         self.in_channels, self.num_classes, self.base_c = in_channels, num_classes, base_c
@@ -311,6 +312,10 @@ class AttentionASPPUNet(nn.Module):
 
     def num_launches(self) -> int:
         return _capi.lib().aau_num_launches(self._handle) if self._handle is not None else 0
+
+    def last_forward_was_graph(self) -> bool:
+        """True when the last forward went out as one CUDA-graph launch (small batches; ``set_option("graph", 0 / 1 / -1)``)."""
+        return bool(_capi.lib().aau_last_forward_was_graph(self._handle)) if self._handle is not None else False
 
     def op_profile(self):
         """Per-launch records of the last forward: ``[{layer, kernel, ms, flops, bytes}]`` (``ms`` is -1 unless

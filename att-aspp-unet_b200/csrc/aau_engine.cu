@@ -99,8 +99,16 @@ struct Plan {
     std::vector<OpInfo> info;
     std::vector<cudaEvent_t> events;     // profile mode: ops.size()+1 events
     std::map<std::string, View> named;
+    // CUDA-graph replay (small batches): the launch sequence is captured once per input type against plan-owned input /
+    // output buffers, so the caller's pointers never enter the graph (copied in / out around the replay)
+    void* g_in = nullptr;                // B*H*W*4 bytes (u8 frames use the first quarter)
+    float *g_logits = nullptr, *g_psi3 = nullptr, *g_psi2 = nullptr;
+    cudaGraphExec_t g_exec[2] = {nullptr, nullptr};   // by x_dtype
+    bool g_failed = false;
     ~Plan() {
         for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+        for (cudaGraphExec_t g : g_exec)
+            if (g) cudaGraphExecDestroy(g);
     }
 };
 
@@ -124,6 +132,10 @@ struct Engine {
     int* d_err = nullptr;
     cudaStream_t side_stream = nullptr;               // ASPP image-pooling branch (fork / join around the conv branches)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t graph_stream = nullptr;              // graph replays run here (a legacy default stream cannot be captured)
+    cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+    int opt_graph = -1;       // CUDA-graph replay of the forward: -1 auto (batches of at most graph_max_px pixels), 0 never, 1 always
+    int opt_graph_max_px = 4 * 562 * 744;
     int opt_side = 1;
     int opt_pdl = 1;
     int opt_fusefix = 1;
@@ -139,6 +151,7 @@ struct Engine {
     int opt_mt_shape = 1;     // the tile-shape search knows about stacked M-blocks (padding of th * 2 rows)
     int opt_dxn_full = 1;     // dx-stacked layers whose un-split weights are 112..144 KB: keep them resident beside 32-channel A slabs
     int last_launches = 0;
+    int last_replayed = 0;    // the last forward went out as one graph launch
     int opt_amode = -1;
     int opt_resident = 1;
     int opt_fusepool = 1;
@@ -1056,6 +1069,12 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
         bias_img = (float*)bump.take((size_t)B * oc * sizeof(float));
         gap_partial = (float*)bump.take((size_t)B * 16 * 8 * c * sizeof(float));
     }
+    plan.g_in = bump.take((size_t)B * H * W * 4);
+    plan.g_logits = (float*)bump.take((size_t)B * H * W * 4);
+    if (!e.pipeline()) {
+        plan.g_psi3 = (float*)bump.take((size_t)B * Hs[4] * Ws[4] * 4);
+        plan.g_psi2 = (float*)bump.take((size_t)B * Hs[3] * Ws[3] * 4);
+    }
     *need_bytes = bump.off + 1024;
     if (dry) return AAU_OK;
 
@@ -1335,7 +1354,8 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
     if (!cfg || !out) { g_create_error = "null argument"; return AAU_ERR_INVALID; }
     *out = nullptr;
     if (cfg->in_channels != 1 || cfg->num_classes != 1) { g_create_error = "only in_channels=1, num_classes=1 are supported"; return AAU_ERR_INVALID; }
-    if (cfg->base_c < 16 || cfg->base_c % 16) { g_create_error = "base_c must be a positive multiple of 16"; return AAU_ERR_INVALID; }
+    // up to 64: the deepest gate's F_int = 4 * base_c channels (pipeline flavour) must fit one 256-column accumulator tile
+    if (cfg->base_c < 16 || cfg->base_c % 16 || cfg->base_c > 64) { g_create_error = "base_c must be 16, 32, 48 or 64"; return AAU_ERR_INVALID; }
     if (cfg->variant != AAU_VARIANT_PIPELINE && cfg->variant != AAU_VARIANT_ABLATION) { g_create_error = "unknown variant"; return AAU_ERR_INVALID; }
     if (cfg->act_dtype != AAU_ACT_BF16 && cfg->act_dtype != AAU_ACT_FP16) { g_create_error = "unknown act_dtype"; return AAU_ERR_INVALID; }
     int ndev = 0;
@@ -1372,7 +1392,10 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
     }
     if (cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e.graph_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.ev_gin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.ev_gout, cudaEventDisableTiming) != cudaSuccess) {
         g_create_error = "cannot create the side stream";
         delete h;
         return AAU_ERR_CUDA;
@@ -1403,6 +1426,10 @@ int aau_destroy(aau_handle* h) {
     if (h->e.side_stream) cudaStreamDestroy(h->e.side_stream);
     if (h->e.ev_fork) cudaEventDestroy(h->e.ev_fork);
     if (h->e.ev_join) cudaEventDestroy(h->e.ev_join);
+    h->e.plans.clear();                                          // graph executables go before their streams
+    if (h->e.graph_stream) cudaStreamDestroy(h->e.graph_stream);
+    if (h->e.ev_gin) cudaEventDestroy(h->e.ev_gin);
+    if (h->e.ev_gout) cudaEventDestroy(h->e.ev_gout);
     delete h;
     return AAU_OK;
 }
@@ -1491,12 +1518,51 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
     }
     FwdArgs a{x, x_dtype, logits, psi3, psi2, (cudaStream_t)stream};
     const bool prof = e.opt_profile != 0;
+    const bool want_graph = !prof && !plan->g_failed && e.graph_stream != nullptr &&
+                            (e.opt_graph == 1 || (e.opt_graph < 0 && (long long)B * H * W <= (long long)e.opt_graph_max_px));
+    bool replayed = false;
+    if (want_graph) {
+        // Small batches are launch-bound (29 launches of a few microseconds each): replay them as ONE graph launch.
+        const size_t in_bytes = (size_t)B * H * W * (x_dtype == AAU_X_U8 ? 1 : 4);
+        const size_t psi3_bytes = (size_t)B * (H / 8) * (W / 8) * 4, psi2_bytes = (size_t)B * (H / 4) * (W / 4) * 4;
+        cudaStream_t gs = e.graph_stream;
+        if (!plan->g_exec[x_dtype]) {
+            FwdArgs ga{plan->g_in, x_dtype, plan->g_logits, plan->g_psi3, plan->g_psi2, gs};
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                for (auto& op : plan->ops)
+                    if (op(ga) != cudaSuccess) { ok = false; break; }
+                ok = (cudaStreamEndCapture(gs, &graph) == cudaSuccess) && ok && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&plan->g_exec[x_dtype], graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {                                               // this driver cannot capture the sequence: plain launches from now on
+                cudaGetLastError();
+                plan->g_exec[x_dtype] = nullptr;
+                plan->g_failed = true;
+            }
+        }
+        if (plan->g_exec[x_dtype]) {
+            AAU_CUDA(cudaEventRecord(e.ev_gin, a.stream));           // the caller's stream hands over to the replay stream and back
+            AAU_CUDA(cudaStreamWaitEvent(gs, e.ev_gin, 0));
+            AAU_CUDA(cudaMemcpyAsync(plan->g_in, x, in_bytes, cudaMemcpyDeviceToDevice, gs));
+            AAU_CUDA(cudaGraphLaunch(plan->g_exec[x_dtype], gs));
+            AAU_CUDA(cudaMemcpyAsync(logits, plan->g_logits, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice, gs));
+            if (psi3 && plan->g_psi3 && e.has_gate(4)) AAU_CUDA(cudaMemcpyAsync(psi3, plan->g_psi3, psi3_bytes, cudaMemcpyDeviceToDevice, gs));
+            if (psi2 && plan->g_psi2 && e.has_gate(3)) AAU_CUDA(cudaMemcpyAsync(psi2, plan->g_psi2, psi2_bytes, cudaMemcpyDeviceToDevice, gs));
+            AAU_CUDA(cudaEventRecord(e.ev_gout, gs));
+            AAU_CUDA(cudaStreamWaitEvent(a.stream, e.ev_gout, 0));
+            replayed = true;
+        }
+    }
     if (prof && plan->events.size() != plan->ops.size() + 1) {
         plan->events.resize(plan->ops.size() + 1);
         for (auto& ev : plan->events) AAU_CUDA(cudaEventCreate(&ev));
     }
     int n = 0;
     for (auto& op : plan->ops) {
+        if (replayed) break;
         if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
         cudaError_t r = op(a);
         if (r != cudaSuccess) return e.fail(AAU_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(r));
@@ -1518,6 +1584,7 @@ int aau_forward(aau_handle* h, const void* x, int x_dtype, int B, int H, int W, 
         ++n;
     }
     if (prof) AAU_CUDA(cudaEventRecord(plan->events[n], a.stream));
+    e.last_replayed = replayed ? 1 : 0;
     int kernels = 0;                                                 // stream-ordering ops (the side-stream join) are not kernel launches
     for (const OpInfo& oi : plan->info) kernels += oi.kernel.empty() || oi.kernel[0] != '(' ? 1 : 0;
     e.last_launches = kernels;
@@ -1648,6 +1715,24 @@ int aau_tta_prob(aau_handle* h, const float* logits, const float* logits_of_flip
     return AAU_OK;
 }
 
+int aau_best_frame_mask(aau_handle* h, const float* values, int input_kind, int N, int H, int W, float prob_thr, const int32_t* best,
+                        uint8_t* mask, void* stream) {
+    if (!h) return AAU_ERR_INVALID;
+    Engine& e = h->e;
+    if (!values || !best || !mask || N < 1 || H < 1 || W < 1) return e.fail(AAU_ERR_INVALID, "bad best_frame_mask arguments");
+    if (input_kind != AAU_IN_LOGITS && input_kind != AAU_IN_PROB && input_kind != AAU_IN_LOGIT_CUT) return e.fail(AAU_ERR_INVALID, "unknown input_kind");
+    cudaSetDevice(e.device);
+    float cut = prob_thr;
+    if (input_kind == AAU_IN_LOGITS) {
+        if (e.cut_thr != prob_thr) { e.cut_val = logit_cutoff(prob_thr); e.cut_thr = prob_thr; }
+        cut = e.cut_val;
+    }
+    const int HW = H * W;
+    best_frame_mask_kernel<<<std::max(1, std::min(e.num_sms * 4, (HW + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(values, HW, cut, best, mask);
+    AAU_CUDA(cudaGetLastError());
+    return AAU_OK;
+}
+
 int aau_resize_u8(aau_handle* h, const uint8_t* src, int N, int SH, int SW, uint8_t* dst, int DH, int DW, void* stream) {
     if (!h) return AAU_ERR_INVALID;
     Engine& e = h->e;
@@ -1696,6 +1781,7 @@ int aau_device_fault(aau_handle* h) {
 }
 
 int aau_num_launches(const aau_handle* h) { return h ? h->e.last_launches : 0; }
+int aau_last_forward_was_graph(const aau_handle* h) { return h ? h->e.last_replayed : 0; }
 int aau_num_ops(const aau_handle* h) { return (h && h->e.last_plan) ? (int)h->e.last_plan->ops.size() : 0; }
 
 int aau_op_profile(aau_handle* h, int i, const char** layer, const char** kernel, float* ms, double* flops, double* bytes) {
@@ -1747,6 +1833,10 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         e.opt_profile = value;
         return AAU_OK;
     }
+    if (n == "graph_max_px") {
+        e.opt_graph_max_px = value;
+        return AAU_OK;
+    }
     if (n == "keep_sum" || n == "stem_lo") {                         // weight-preparation options: re-fold and re-upload
         (n == "keep_sum" ? e.opt_keep_sum : e.opt_stem_lo) = value;
         if (e.committed) {
@@ -1760,7 +1850,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
         {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"tb", &e.opt_tb}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
-        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}};
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}};
     for (const auto& o : plan_options) {
         if (n == o.first) {
             *o.second = value;

@@ -400,6 +400,17 @@ __global__ void __launch_bounds__(256) frame_sum_u8_kernel(const uint8_t* __rest
     }
 }
 
+// {0,1} mask of the frame the argmax picked, without the index ever visiting the host: best[0] = frame, best[1] = its area
+// (all-zero mask when the area is 0, model_attention_aspp.py:75-76).  Lets a sweep's whole device part be enqueued in one go,
+// so the host tail of one sweep (connected components of this one mask) overlaps the kernels of the next sweep.
+__global__ void __launch_bounds__(256) best_frame_mask_kernel(const float* __restrict__ values, int HW, float cut, const int* __restrict__ best,
+                                                              uint8_t* __restrict__ mask) {
+    const int frame = best[0], area = best[1];
+    const float* src = values + (size_t)frame * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+        mask[i] = area > 0 ? (uint8_t)(__ldg(src + i) > cut) : (uint8_t)0;
+}
+
 // first index of the maximum area (numpy argmax tie-break); out[0] = index, out[1] = area at that index
 __global__ void __launch_bounds__(1024) area_argmax_kernel(const int* __restrict__ areas, int n, int* __restrict__ out) {
     int best = -1, best_i = 0x7fffffff;

@@ -220,16 +220,36 @@ class FetalAbdomenSegmentation:
         _capi.check(hnd, st, "aau_condition_frames")
         return out
 
+    # ------------------------------------------------------------------------------------------------
+    # sweep driver: everything a sweep needs from the device is ENQUEUED by _enqueue_sweep (no host synchronisation), the
+    # host tail (one D2H wait + connected components of ONE mask) runs in _finish_sweep.  segment_sweep = both back to back;
+    # segment_sweeps pipelines them so that the host tail of sweep k overlaps the kernels of sweep k + 1.
+    class _Slot:
+        """Per-sweep device / pinned-host buffers (two slots alternate so that a finished sweep can still be read while
+        the next one is running)."""
+
+        def __init__(self):
+            self.logits = self.scores = self.mask = self.h_scores = self.h_mask = None
+            self.done = torch.cuda.Event()
+
+    def _slot(self, which: int, n: int, H: int, W: int) -> "FetalAbdomenSegmentation._Slot":
+        if getattr(self, "_slots", None) is None:
+            self._slots = [None, None]
+        sl = self._slots[which]
+        if sl is None:
+            sl = self._slots[which] = FetalAbdomenSegmentation._Slot()
+        dev = self.device
+        # every frame's logits stay resident (1.67 MB per 562x744 frame; 1.4 GB per 840-frame sweep of 180 GB)
+        if sl.logits is None or sl.logits.shape != (max(n, 1), 1, H, W):
+            sl.logits = torch.empty((max(n, 1), 1, H, W), dtype=torch.float32, device=dev)
+            sl.scores = torch.zeros(max(n, 1) + 2, dtype=torch.int32, device=dev)   # areas[n] | {best index, best area}: ONE D2H copy
+            sl.mask = torch.empty((H, W), dtype=torch.uint8, device=dev)
+            sl.h_scores = torch.empty(max(n, 1) + 2, dtype=torch.int32).pin_memory()
+            sl.h_mask = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+        return sl
+
     @torch.no_grad()
-    def segment_sweep(self, volume, frame_range: Optional[Tuple[int, int]] = None, prob_thr: Optional[float] = None,
-                      finalize: bool = True, condition: bool = False):
-        """Segment ``volume[frame_range]`` (``uint8`` or float ``[N,H,W]``, host numpy / pinned tensor) and select
-        the best frame.  Returns a dict: ``areas`` (int32 numpy, this shard), ``best_idx`` (index into the full
-        sweep, -1 if empty), ``best_area``, ``mask`` (uint8 [H,W], post-processed as the reference) and timing
-        counters.  With ``finalize=False`` only ``areas`` are produced (multi-GPU shards: the caller gathers them,
-        picks the global frame with :func:`merge_shard_scores` and asks the owner rank for :meth:`frame_mask`).
-        ``condition=True`` (uint8 sweeps) runs the reference's frame conditioning on the device between the H2D copy
-        and the network, so a RAW sweep goes in."""
+    def _enqueue_sweep(self, volume, frame_range, prob_thr, finalize, condition, which: int = 0) -> dict:
         thr = self.PROB_THRESHOLD if prob_thr is None else float(prob_thr)
         vol = torch.from_numpy(volume) if isinstance(volume, np.ndarray) else volume
         lo, hi = (0, vol.shape[0]) if frame_range is None else frame_range
@@ -238,24 +258,23 @@ class FetalAbdomenSegmentation:
         is_u8 = vol.dtype == torch.uint8
         if not is_u8:
             vol = vol.float()
-        scores = torch.zeros(max(n, 1) + 2, dtype=torch.int32, device=dev)   # areas[n] | {best index, best area}: ONE D2H copy
-        areas, best = scores[: max(n, 1)], scores[max(n, 1):]
+        sl = self._slot(which, n, H, W)
+        areas, best = sl.scores[: max(n, 1)], sl.scores[max(n, 1):]
         B = max(1, min(self.batch, n))
-        # every frame's logits stay resident (1.67 MB per 562x744 frame; 1.4 GB per 840-frame sweep of 180 GB)
-        if getattr(self, "_logits_all", None) is None or self._logits_all.shape != (max(n, 1), 1, H, W):
-            self._logits_all = torch.empty((max(n, 1), 1, H, W), dtype=torch.float32, device=dev)
-        logits_all = self._logits_all
+        self._logits_all = sl.logits
         # double-buffered pinned staging -> device input, copies on a side stream
         shape = (2, B, H, W) if is_u8 else (2, B, 1, H, W)
+        main = torch.cuda.current_stream(dev)
         if self._pinned is None or self._pinned.shape != torch.Size(shape) or self._pinned.dtype != vol.dtype:
+            main.synchronize()                                           # a sweep still in flight may be reading the old staging
             self._pinned = torch.empty(shape, dtype=vol.dtype).pin_memory()
             self._staging = torch.empty(shape, dtype=vol.dtype, device=dev)
+            self._batch_no = 0
         if getattr(self, "_copy_stream", None) is None:                # stream and events live as long as the wrapper
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._events = [torch.cuda.Event() for _ in range(4)]
+            self._batch_no = 0
         copy_stream = self._copy_stream
-        main = torch.cuda.current_stream(dev)
-        copy_stream.wait_stream(main)                                   # a previous call's kernels are done with the staging slots
         ready, consumed = self._events[:2], self._events[2:]
         h2d = 0
         starts = list(range(0, n, B))
@@ -263,17 +282,19 @@ class FetalAbdomenSegmentation:
         def stage(i):
             s = starts[i]
             b = min(B, n - s)
-            slot = i & 1
+            k = self._batch_no + i                                       # batches are numbered across sweeps: slot k & 1 was last used by batch k - 2
+            slot = k & 1
             src = vol[lo + s: lo + s + b]
             if vol.is_pinned():
                 host = src if is_u8 else src.unsqueeze(1)
             else:
                 host = self._pinned[slot, :b]
-                consumed[slot].synchronize() if i >= 2 else None      # the pinned slot must have been copied out
+                if k >= 2:
+                    consumed[slot].synchronize()                         # the pinned slot must have been copied out
                 host.copy_(src if is_u8 else src.unsqueeze(1))
             with torch.cuda.stream(copy_stream):
-                if i >= 2:
-                    copy_stream.wait_event(consumed[slot])
+                if k >= 2:
+                    copy_stream.wait_event(consumed[slot])               # the kernels that read this device slot are done
                 self._staging[slot, :b].copy_(host, non_blocking=True)
                 ready[slot].record(copy_stream)
             return b
@@ -281,9 +302,7 @@ class FetalAbdomenSegmentation:
         if starts:
             nb = stage(0)
         for i, s in enumerate(starts):
-            b, slot = nb, i & 1
-            if i + 1 < len(starts):
-                nb = stage(i + 1)
+            b, slot = nb, (self._batch_no + i) & 1
             main.wait_event(ready[slot])
             x = self._staging[slot, :b]
             h2d += x.numel() * x.element_size()
@@ -293,28 +312,72 @@ class FetalAbdomenSegmentation:
                 if getattr(self, "_cond_out", None) is None or self._cond_out.shape != self._staging.shape[1:]:
                     self._cond_out = torch.empty(self._staging.shape[1:], dtype=torch.uint8, device=dev)
                 x = self.condition_on_device(x, out=self._cond_out[:b])
-            logits = self._net_logits(x, out=logits_all[s: s + b])
+            logits = self._net_logits(x, out=sl.logits[s: s + b])
             consumed[slot].record(main)
+            if i + 1 < len(starts):
+                nb = stage(i + 1)                                        # (after `consumed` of the batch two back has been recorded)
             self._scores.run(logits[:, 0], _capi.AAU_IN_LOGITS, thr, areas[s: s + b], None, None)
-        out = {"n_frames": n, "h2d_bytes": h2d, "launches": len(starts) * (self.net.num_launches() + 1) + 2}
+        self._batch_no += len(starts)
+        job = {"n": n, "lo": lo, "H": H, "W": W, "thr": thr, "finalize": finalize, "slot": sl, "h2d": h2d,
+               "launches": len(starts) * (self.net.num_launches() + 1) + 2}
+        if n == 0:
+            return job
+        self._scores.best(areas[:n], best)
+        if finalize:                                                     # the selected frame's mask, picked on the device
+            hnd = self.net.engine_handle()
+            st = _capi.lib().aau_best_frame_mask(hnd, sl.logits.data_ptr(), _capi.AAU_IN_LOGIT_CUT, n, H, W, C.c_float(logit_cutoff(thr)),
+                                                 best.data_ptr(), sl.mask.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _capi.check(hnd, st, "aau_best_frame_mask")
+            sl.h_mask.copy_(sl.mask, non_blocking=True)
+        sl.h_scores.copy_(sl.scores, non_blocking=True)                  # D2H: 4*n + 8 bytes (+ H*W mask bytes), no host sync here
+        sl.done.record(main)
+        return job
+
+    def _finish_sweep(self, job: dict) -> dict:
+        n, lo, H, W, sl = job["n"], job["lo"], job["H"], job["W"], job["slot"]
+        out = {"n_frames": n, "h2d_bytes": job["h2d"], "launches": job["launches"]}
         if n == 0:
             out.update(areas=np.zeros(0, np.int32), best_idx=-1, best_area=0, mask=np.zeros((H, W), np.uint8), d2h_bytes=0)
             return out
-        self._scores.best(areas[:n], best)
-        host_scores = scores.cpu().numpy()                   # D2H: 4*n + 8 bytes in one copy, synchronises
-        host_areas = host_scores[:n].copy()
+        sl.done.synchronize()
+        host_scores = sl.h_scores.numpy()
         bi, ba = int(host_scores[-2]), int(host_scores[-1])
-        out.update(areas=host_areas, best_area=ba, best_local=bi, d2h_bytes=4 * n + 8)
-        if not finalize:
+        out.update(areas=host_scores[:n].copy(), best_area=ba, best_local=bi, d2h_bytes=4 * n + 8)
+        if not job["finalize"]:
             return out
         if ba == 0:
             out.update(best_idx=-1, mask=np.zeros((H, W), np.uint8))
             return out
-        out["mask"] = self._mask_from_logits(logits_all[bi].reshape(1, H, W), thr)
+        out["mask"] = largest_component(sl.h_mask.numpy())               # host integer work on ONE frame (model_attention_aspp.py:80-85)
         out["d2h_bytes"] += H * W
         out["best_idx"] = lo + bi
         self.last = out
         return out
+
+    def segment_sweep(self, volume, frame_range: Optional[Tuple[int, int]] = None, prob_thr: Optional[float] = None,
+                      finalize: bool = True, condition: bool = False):
+        """Segment ``volume[frame_range]`` (``uint8`` or float ``[N,H,W]``, host numpy / pinned tensor) and select
+        the best frame.  Returns a dict: ``areas`` (int32 numpy, this shard), ``best_idx`` (index into the full
+        sweep, -1 if empty), ``best_area``, ``mask`` (uint8 [H,W], post-processed as the reference) and timing
+        counters.  With ``finalize=False`` only ``areas`` are produced (multi-GPU shards: the caller gathers them,
+        picks the global frame with :func:`merge_shard_scores` and asks the owner rank for :meth:`frame_mask`).
+        ``condition=True`` (uint8 sweeps) runs the reference's frame conditioning on the device between the H2D copy
+        and the network, so a RAW sweep goes in."""
+        return self._finish_sweep(self._enqueue_sweep(volume, frame_range, prob_thr, finalize, condition, which=0))
+
+    def segment_sweeps(self, volumes, prob_thr: Optional[float] = None, condition: bool = False):
+        """Generator over the results of ``segment_sweep`` for a sequence of cases, software-pipelined: the device part of
+        case k + 1 is enqueued before the host waits for case k, so the host tail (the D2H wait and the connected
+        components of the selected frame) overlaps the next case's kernels.  Same results as calling ``segment_sweep`` per
+        case (many-case inference, BASELINE config[2])."""
+        pending = None
+        for k, vol in enumerate(volumes):
+            job = self._enqueue_sweep(vol, None, prob_thr, True, condition, which=k & 1)
+            if pending is not None:
+                yield self._finish_sweep(pending)
+            pending = job
+        if pending is not None:
+            yield self._finish_sweep(pending)
 
     @torch.no_grad()
     def predict(self, input_img_path, save_probabilities: bool = False) -> np.ndarray:

@@ -46,7 +46,7 @@ enum { AAU_IN_LOGITS = 0, AAU_IN_PROB = 1, AAU_IN_U8 = 2, AAU_IN_LOGIT_CUT = 3 }
 typedef struct {
     int32_t in_channels;   /* must be 1 */
     int32_t num_classes;   /* must be 1 */
-    int32_t base_c;        /* multiple of 16 (reference uses 16, 32, 48) */
+    int32_t base_c;        /* 16, 32, 48 or 64 (reference uses 16, 32, 48) */
     int32_t variant;       /* AAU_VARIANT_* */
     int32_t use_att;       /* ablation only */
     int32_t use_aspp;      /* ablation only */
@@ -112,6 +112,13 @@ int aau_frame_scores(aau_handle* h, const void* values, int input_kind, int N, i
  * aau_frame_scores calls of a sweep, and on the host-gathered scores of a multi-GPU run.  Asynchronous. */
 int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, void* stream);
 
+/* {0,1} mask (device uint8 [H,W]) of the frame an earlier aau_best_frame / aau_frame_scores call selected: `best` is that call's
+ * device int32 [2] result, read ON THE DEVICE, so the index never has to visit the host between the two calls; an area of 0
+ * gives the all-zero mask (model_attention_aspp.py:75-76).  `values` / `input_kind` / `prob_thr` as in aau_frame_scores
+ * (float kinds only).  With it a sweep's whole device part is enqueued without a host synchronisation.  Asynchronous. */
+int aau_best_frame_mask(aau_handle* h, const float* values, int input_kind, int N, int H, int W, float prob_thr,
+                        const int32_t* best, uint8_t* mask, void* stream);
+
 /* prob[i] = 1 / (1 + exp(-logits[i])), device fp32 -> device fp32, n elements: the `torch.sigmoid(self.net(x))` of
  * model_attention_aspp.py:54 for callers that want the probability volume itself (`predict`).  Asynchronous. */
 int aau_sigmoid(aau_handle* h, const float* logits, int64_t n, float* prob, void* stream);
@@ -151,6 +158,7 @@ int aau_device_fault(aau_handle* h);
 
 /* Debug / measurement aids. */
 int aau_num_launches(const aau_handle* h);          /* kernels launched by the last aau_forward */
+int aau_last_forward_was_graph(const aau_handle* h);   /* 1 when the last aau_forward replayed its kernels as ONE CUDA-graph launch */
 int aau_num_ops(const aau_handle* h);               /* stream operations of the last aau_forward: its kernels plus stream-ordering
                                                         steps (the side-stream join of the ASPP image-pooling branch) */
 /* Per-operation record of the LAST aau_forward: i in [0, aau_num_ops).  `layer` = the reference layer the
@@ -177,6 +185,10 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *              (both re-run the weight preparation: they synchronise the device)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
  *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
+ *   "graph"    CUDA-graph replay of the forward's launch sequence: -1 auto (batches of at most "graph_max_px" = B*H*W pixels,
+ *              default 4 * 562 * 744: the launch-bound small-batch regime), 0 never, 1 always.  The sequence is captured once
+ *              per (shape, workspace, input type) against library-owned input / output buffers in the workspace; a replay is
+ *              copy-in, ONE graph launch, copy-out on a library-owned stream joined to the caller's stream by events.
  *   "profile"  0/1 record CUDA events around every launch of the following forwards (aau_op_profile). */
 int aau_set_option(aau_handle* h, const char* name, int value);
 
