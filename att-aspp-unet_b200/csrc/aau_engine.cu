@@ -51,6 +51,7 @@ struct GemmW {                // packed GEMM operand, device resident
     float* dvec = nullptr;    // optional fp32 vector (gate w_psi, out_conv w)
     float scalar = 0.f;       // optional scalar (gate b_psi, out_conv b)
     int N = 0, K = 0, Cin = 0, taps = 1;
+    int alg_taps = 0;         // taps of the layer as the reference defines it when the packed operand carries structural zeros (0: == taps)
 };
 
 struct View {                 // NHWC 16-bit tensor view inside a (possibly concatenated) buffer
@@ -145,6 +146,8 @@ struct Engine {
     int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
     int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N
                               // layers, bit 3 resident-weight transposed convs (HBM-bound: measured neutral, off by default)
+    int opt_tapskip = 1;      // per-tap staged 3x3 layers skip taps whose box lies outside the image (igemm_tc.cuh: tap_outside)
+    int opt_aspp_merge = 1;   // ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 with dilation > image
     int opt_keep_sum = 1;     // 3x3 weights rounded with the window-sum-preserving rule (weight-preparation option: takes effect at commit)
     int opt_stem_lo = 1;      // tensor-core stem carries the weights' low-order 16-bit term in a second MMA
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
@@ -372,13 +375,14 @@ static int finish_gemm16(Engine& e, GemmW& g, const std::vector<uint16_t>& b16, 
 
 // ConvBNReLU (3x3) or a BN-folded 1x1: B[o][tap*Cin + i] = W[o][i][ky][kx] * s[o]
 static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::string& wkey, const std::string& bnp,
-                        int cin, int cout, int taps) {
+                        int cin, int cout, int taps, bool embed_in_3x3 = false) {
     const std::vector<float>* w = P.get(wkey);
     if (!w) return AAU_OK;   // reported once by the caller through P.missing
     std::vector<double> s, t;
     P.bn(bnp, cout, s, t);
     GemmW g;
     g.N = cout; g.Cin = cin; g.taps = taps; g.K = taps * cin;
+    if (embed_in_3x3) { g.taps = 9; g.K = 9 * cin; g.alg_taps = 1; }               // a 1x1 kernel as the centre tap of a 3x3 one (zeros elsewhere)
     // folded weights rounded ONCE to the 16-bit storage type; 3x3 windows with the sum-preserving rounding above
     const bool f16 = e.is_fp16();
     std::vector<uint16_t> wq((size_t)cout * cin * taps), b16((size_t)g.N * g.K);
@@ -394,7 +398,7 @@ static int prep_conv_bn(Engine& e, Prep& P, const std::string& name, const std::
             } else {
                 for (int tp = 0; tp < taps; ++tp) wq[base + tp] = to16((float)((double)(*w)[base + tp] * s[o]), f16);
             }
-            for (int tp = 0; tp < taps; ++tp) b16[(size_t)o * g.K + (size_t)tp * cin + i] = wq[base + tp];
+            for (int tp = 0; tp < taps; ++tp) b16[(size_t)o * g.K + (size_t)(embed_in_3x3 ? 4 : tp) * cin + i] = wq[base + tp];
         }
     }
     int r = finish_gemm16(e, g, b16, bias);
@@ -476,6 +480,7 @@ static int commit_weights(Engine& e) {
     const int ic = 8 * c, oc = 16 * c;
     if (e.has_aspp()) {
         if ((r = prep_conv_bn(e, P, "aspp.0", "bridge.blocks.0.0.weight", "bridge.blocks.0.1", ic, oc, 1))) return r;
+        if ((r = prep_conv_bn(e, P, "aspp.0e", "bridge.blocks.0.0.weight", "bridge.blocks.0.1", ic, oc, 1, true))) return r;
         for (int i = 1; i <= 3; ++i)
             if ((r = prep_conv_bn(e, P, "aspp." + std::to_string(i), "bridge.blocks." + std::to_string(i) + ".0.weight",
                                   "bridge.blocks." + std::to_string(i) + ".1", ic, oc, 9)))
@@ -892,6 +897,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.b_region_bytes = b_region;
     P.is_fp16 = e.is_fp16() ? 1 : 0;
     P.tile_iter = e.opt_titer;
+    P.skip_oob = (e.opt_tapskip != 0 && P.amode == AMODE_TAP && d0.w->taps == 9) ? 1 : 0;
     P.lean_sync = e.opt_lean;
     P.err = e.d_err;
     P.nprob = (int)descs.size();
@@ -979,8 +985,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             oi.bytes += px * d.in.C * 2 + (double)d.in.C * 4 * d.convt_cout * 2 + (double)d.out.B * d.out.H * d.out.W * d.convt_cout * 2;
             continue;
         }
-        oi.flops += 2.0 * px * d.w->K * d.w->N;
-        oi.bytes += px * d.in.C * 2 + (double)d.w->K * d.w->N * 2;
+        const double alg_k = d.w->alg_taps ? (double)d.w->alg_taps * d.w->Cin : (double)d.w->K;   // algorithmic depth (no structural zeros)
+        oi.flops += 2.0 * px * alg_k * d.w->N;
+        oi.bytes += px * d.in.C * 2 + alg_k * d.w->N * 2;
         if (d.epi == EPI_STORE) oi.bytes += px * d.w->N * 2;
         if (d.pool_out.p) oi.bytes += px * d.w->N * 2 / 4;
         if (d.epi == EPI_CONVT) oi.bytes += px * d.w->N * 2;
@@ -1224,23 +1231,29 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
                 return r;
             });
         }
-        // the four conv branches in ONE launch, each writing its slice of the concatenated tensor
+        // the four conv branches, each writing its slice of the concatenated tensor.  The 1x1 branch has a different K extent
+        // than the dilated ones: it either gets its own launch, or (default) rides in theirs as a 3x3 kernel whose only
+        // non-zero tap is the centre and whose dilation puts the other eight taps outside every tile -- the kernel skips such
+        // taps (tap_outside), so it costs its one tap and no launch of its own.
         const int rates[4] = {1, 6, 12, 18};
-        // the 1x1 branch has a different K extent, so it gets its own launch; the three dilated branches share one
+        const bool merge0 = e.opt_aspp_merge != 0 && e.opt_tapskip != 0 && e.gw.count("aspp.0e") != 0;
+        std::vector<ConvDesc> dil3;
         {
             ConvDesc d;
-            d.w = &e.gw.at("aspp.0");
+            d.w = &e.gw.at(merge0 ? "aspp.0e" : "aspp.0");
             d.in = pl[4]; d.out = sub_view(asppcat, 0, oc); d.epi = EPI_STORE; d.relu = 1;
-            if ((r = add_igemm(e, plan, "bridge.blocks.0", {d}, 0))) return r;
+            if (merge0) {
+                d.dil = std::max(Hs[5], Ws[5]) + 256;                         // beyond any tile: |offset| >= image extent + tile extent
+                dil3.push_back(d);
+            } else if ((r = add_igemm(e, plan, "bridge.blocks.0", {d}, 0))) return r;
         }
-        std::vector<ConvDesc> dil3;
         for (int i = 1; i <= 3; ++i) {
             ConvDesc d;
             d.w = &e.gw.at("aspp." + std::to_string(i));
             d.in = pl[4]; d.out = sub_view(asppcat, i * oc, oc); d.dil = rates[i]; d.epi = EPI_STORE; d.relu = 1;
             dil3.push_back(d);
         }
-        if ((r = add_igemm(e, plan, "bridge.blocks.1-3", dil3, 0))) return r;
+        if ((r = add_igemm(e, plan, merge0 ? "bridge.blocks.0-3" : "bridge.blocks.1-3", dil3, 0))) return r;
         {
             ConvDesc d;
             d.w = &e.gw.at("aspp.project");
@@ -1850,7 +1863,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
         {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"tb", &e.opt_tb}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
-        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}};
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}, {"tapskip", &e.opt_tapskip}, {"aspp_merge", &e.opt_aspp_merge}};
     for (const auto& o : plan_options) {
         if (n == o.first) {
             *o.second = value;

@@ -168,6 +168,7 @@ struct alignas(64) IgemmParams {
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int pair_order;         // CTA pairs over several N tiles: consecutive tiles are two M tiles of one N tile
     int TB;                 // images per tile (per-tap staging of small images: the TMA boxes span TB frames of TH rows each)
+    int skip_oob;           // per-tap staging, 3x3: taps whose whole box lies outside the image (dilated ASPP branches) are not issued
     int* err;
 };
 
@@ -336,6 +337,17 @@ __device__ __forceinline__ void tap_offsets(const IgemmProblem& q, int tap, int&
     else if (q.taps == 2) { dy = q.fix_axis == 0 ? tap - 1 : 0; dx = q.fix_axis == 1 ? tap - 1 : 0; }
 }
 
+// Per-tap staging of a (dilated) 3x3 convolution: a tap whose whole TH x TW box lies outside the image would read nothing but
+// TMA zero fill and add exact zeros -- neither its boxes nor its weight sub-blocks are fetched, none of its MMAs issued.  At
+// 35 x 46 this is 58 % of the taps of the dilation-18 branch and 22 % of the dilation-12 one; a 1x1 convolution embedded as
+// the centre tap of a 3x3 with a dilation beyond the image (how ASPP's blocks.0 joins the dilated branches' launch) keeps
+// exactly its one tap.  Producer and MMA issuer evaluate the same predicate on the same tile, so the rings stay in step.
+__device__ __forceinline__ bool tap_outside(const IgemmParams& P, const IgemmProblem& q, const TileCoord& tc, int dy, int dx) {
+    if (!P.skip_oob || q.taps != 9) return false;
+    const int ylo = tc.y0 + dy, xlo = tc.x0 + dx;
+    return ylo >= q.H || ylo + P.TH <= 0 || xlo >= q.W || xlo + P.TW <= 0;
+}
+
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
 // field, so stepping K by 32 bytes is "+2" on the low word.
 template <int KK, bool PAIR = false>
@@ -397,6 +409,11 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         if (amode == AMODE_TAP) {
             const int steps = q.taps * q.nchunk;
             for (int s = 0; s < steps; ++s) {
+                if (P.skip_oob) {                                             // (same predicate as the producer's)
+                    int dy, dx;
+                    tap_offsets(q, s / q.nchunk, dy, dx);
+                    if (tap_outside(P, q, tc, dy, dx)) continue;
+                }
                 ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 const int bslot = res ? s : ib;
                 if (!res) ptx::mbar_wait(full_b + 8u * (uint32_t)ib, pb, P.err, ERR_MMA_WAIT_FULL);
@@ -604,6 +621,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         const int ch = s - tap * q.nchunk;
                         int dy, dx;
                         tap_offsets(q, tap, dy, dx);
+                        if (tap_outside(P, q, tc, dy, dx)) continue;          // all zero fill: the MMA issuer skips it too
                         ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (!res) ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (ptx::elect_one()) {

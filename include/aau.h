@@ -185,6 +185,8 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *              (both re-run the weight preparation: they synchronise the device)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
  *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
+ *   "tapskip"  1/0 per-tap staged 3x3 layers (the dilated ASPP branches) skip taps whose whole box lies outside the image
+ *   "aspp_merge" 1/0 ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 (needs "tapskip")
  *   "graph"    CUDA-graph replay of the forward's launch sequence: -1 auto (batches of at most "graph_max_px" = B*H*W pixels,
  *              default 4 * 562 * 744: the launch-bound small-batch regime), 0 never, 1 always.  The sequence is captured once
  *              per (shape, workspace, input type) against library-owned input / output buffers in the workspace; a replay is
