@@ -147,7 +147,7 @@ struct Engine {
     int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N
                               // layers, bit 3 resident-weight transposed convs (HBM-bound: measured neutral, off by default)
     int opt_tapskip = 1;      // per-tap staged 3x3 layers skip taps whose box lies outside the image (igemm_tc.cuh: tap_outside)
-    int opt_aspp_merge = 1;   // ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 with dilation > image
+    int opt_aspp_merge = 0;   // (measured slower: 0.81 vs 0.69 ms, tools/layer_ab.py) ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 with dilation > image
     int opt_keep_sum = 1;     // 3x3 weights rounded with the window-sum-preserving rule (weight-preparation option: takes effect at commit)
     int opt_stem_lo = 1;      // tensor-core stem carries the weights' low-order 16-bit term in a second MMA
     int opt_stem_tc = 1;      // uint8 frames: d1.0 as a K = 16 implicit GEMM on the tensor cores (stem_tc.cuh)
@@ -1232,9 +1232,10 @@ static int build_plan(Engine& e, Plan& plan, int B, int H, int W, void* ws, size
             });
         }
         // the four conv branches, each writing its slice of the concatenated tensor.  The 1x1 branch has a different K extent
-        // than the dilated ones: it either gets its own launch, or (default) rides in theirs as a 3x3 kernel whose only
+        // than the dilated ones: it gets its own launch (default), or ("aspp_merge") rides in theirs as a 3x3 kernel whose only
         // non-zero tap is the centre and whose dilation puts the other eight taps outside every tile -- the kernel skips such
-        // taps (tap_outside), so it costs its one tap and no launch of its own.
+        // taps (tap_outside).  Measured on B200, batch 56 (tools/layer_ab.py): own launch 0.050 + 0.643 ms, merged 0.806 ms --
+        // the one-tap tiles are epilogue-bound and delay the dilated tiles queued behind them -- so the merge stays off.
         const int rates[4] = {1, 6, 12, 18};
         const bool merge0 = e.opt_aspp_merge != 0 && e.opt_tapskip != 0 && e.gw.count("aspp.0e") != 0;
         std::vector<ConvDesc> dil3;

@@ -341,11 +341,16 @@ __device__ __forceinline__ void tap_offsets(const IgemmProblem& q, int tap, int&
 // TMA zero fill and add exact zeros -- neither its boxes nor its weight sub-blocks are fetched, none of its MMAs issued.  At
 // 35 x 46 this is 58 % of the taps of the dilation-18 branch and 22 % of the dilation-12 one; a 1x1 convolution embedded as
 // the centre tap of a 3x3 with a dilation beyond the image (how ASPP's blocks.0 joins the dilated branches' launch) keeps
-// exactly its one tap.  Producer and MMA issuer evaluate the same predicate on the same tile, so the rings stay in step.
-__device__ __forceinline__ bool tap_outside(const IgemmParams& P, const IgemmProblem& q, const TileCoord& tc, int dy, int dx) {
-    if (!P.skip_oob || q.taps != 9) return false;
+// exactly its one tap.  Producer and MMA issuer evaluate the same predicate on the same tile, so the rings stay in step; the
+// two CTAs of a pair share every MMA and every barrier, so there a tap goes only when it lies outside BOTH their tiles
+// (`tcp` = the peer's tile, tile index ^ 1).
+__device__ __forceinline__ bool box_outside(const IgemmParams& P, const IgemmProblem& q, const TileCoord& tc, int dy, int dx) {
     const int ylo = tc.y0 + dy, xlo = tc.x0 + dx;
     return ylo >= q.H || ylo + P.TH <= 0 || xlo >= q.W || xlo + P.TW <= 0;
+}
+__device__ __forceinline__ bool tap_outside(const IgemmParams& P, const IgemmProblem& q, const TileCoord& tc, const TileCoord& tcp, int dy, int dx) {
+    if (!P.skip_oob || q.taps != 9) return false;
+    return box_outside(P, q, tc, dy, dx) && box_outside(P, q, tcp, dy, dx);
 }
 
 // KK tcgen05.mma (K = 16 each) over one KC-wide sub-block.  Descriptors only differ in their 14-bit start-address
@@ -408,11 +413,12 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
         uint32_t accumulate = 0;
         if (amode == AMODE_TAP) {
             const int steps = q.taps * q.nchunk;
+            const TileCoord tcp = (PAIR && P.skip_oob) ? decode_tile(P, it.t ^ 1) : tc;
             for (int s = 0; s < steps; ++s) {
-                if (P.skip_oob) {                                             // (same predicate as the producer's)
+                if (P.skip_oob) {                                             // (same predicate as the producers')
                     int dy, dx;
                     tap_offsets(q, s / q.nchunk, dy, dx);
-                    if (tap_outside(P, q, tc, dy, dx)) continue;
+                    if (tap_outside(P, q, tc, tcp, dy, dx)) continue;
                 }
                 ptx::mbar_wait(full_a + 8u * (uint32_t)ia, pa, P.err, ERR_MMA_WAIT_FULL);
                 const int bslot = res ? s : ib;
@@ -616,12 +622,13 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 const IgemmProblem& q = MULTI ? P.prob[tc.pi] : P.prob[0];   // single-problem launches: fixed parameter offsets
                 if (amode == AMODE_TAP) {
                     const int steps = q.taps * q.nchunk;
+                    const TileCoord tcp = (PAIR && P.skip_oob) ? decode_tile(P, it.t ^ 1) : tc;
                     for (int s = 0; s < steps; ++s) {
                         const int tap = s / q.nchunk;
                         const int ch = s - tap * q.nchunk;
                         int dy, dx;
                         tap_offsets(q, tap, dy, dx);
-                        if (tap_outside(P, q, tc, dy, dx)) continue;          // all zero fill: the MMA issuer skips it too
+                        if (tap_outside(P, q, tc, tcp, dy, dx)) continue;     // all zero fill: the MMA issuer skips it too
                         ptx::mbar_wait(&empty_a[ia], pa ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (!res) ptx::mbar_wait(&empty_b[ib], pb ^ 1, P.err, ERR_PRODUCER_WAIT);
                         if (ptx::elect_one()) {

@@ -364,7 +364,7 @@ OPTION_SETS = [
     {"graph": 1, "pdl": 0},         # graph replay without programmatic dependent launch edges
     {"keep_sum": 0, "stem_lo": 0},  # plain nearest rounding of the 3x3 weights, single-term stem weights
     {"tapskip": 0},                 # dilated ASPP branches issue every tap (zero-filled boxes included), blocks.0 in its own launch
-    {"aspp_merge": 0},              # taps outside the image skipped, blocks.0 still in its own launch
+    {"aspp_merge": 1},              # blocks.0 as an embedded centre tap inside the dilated branches' launch
 ]
 
 
