@@ -764,6 +764,10 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // (without CTA pairs; with them each CTA holds half of the weights, two clusters share an SM pair and row-shifted taps
     // win there too: d2.1 -10 % against the paired dx-stacked form)
     if (rs && dxn && want_pool && (size_t)9 * Cin * BN * 2 > 64 * 1024 && e.opt_amode < 0 && (e.opt_pair & 4) == 0) rs = false;
+    // round 2, with a specialised dx-stacked + out_conv instantiation (B200, batch 56, fp16, tools/layer_ab.py): u1.conv.1 +
+    // out_conv 0.634 ms dx-stacked against 0.672 ms row-shifted -- the row-shifted form sits at its operand-read floor (18
+    // N = 32 MMAs x 36 cycles per tile) while this epilogue stores nothing, so three times fewer MMAs win
+    if (rs && dxn && d0.epi == EPI_OUTCONV && e.opt_amode < 0 && (e.opt_pair & 4) != 0 && e.opt_rs != 2) rs = false;
     if (rs) { dxn = false; n_out = BN; }
     if (dxn || rs) slab = true;                                    // shares the slab geometry code below
     P.amode = rs ? AMODE_RS : (dxn ? AMODE_DXN : (slab ? AMODE_SLAB : AMODE_TAP));

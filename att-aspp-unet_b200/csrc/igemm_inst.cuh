@@ -22,7 +22,8 @@
     X(2, F, false, true, AMODE_RS, EPI_STORE, 2, 1) X(2, F, false, true, AMODE_RS, EPI_STORE, 2, 0) X(4, F, false, true, AMODE_RS, EPI_STORE, 4, 0) X(4, F, false, true, AMODE_RS, EPI_STORE, 4, 1) \
     X(2, F, false, true, AMODE_RS, EPI_OUTCONV, 2, 0) \
     X(2, F, false, true, AMODE_DXN, EPI_STORE, 4, 0) X(2, F, false, true, AMODE_DXN, EPI_STORE, 4, 1) X(2, F, false, true, AMODE_DXN, EPI_STORE, 2, 0) \
-    X(2, F, false, true, AMODE_TAP, EPI_CONVT, 4, 0) X(4, F, false, true, AMODE_TAP, EPI_CONVT, 4, 0)
+    X(2, F, false, true, AMODE_TAP, EPI_CONVT, 4, 0) X(4, F, false, true, AMODE_TAP, EPI_CONVT, 4, 0) \
+    X(2, F, false, true, AMODE_DXN, EPI_OUTCONV, 2, 0) X(2, F, false, true, AMODE_DXN, EPI_STORE, 2, 1)
 
 namespace aau {
 // kernel lookup: nullptr when the table of that translation unit has no such instantiation
