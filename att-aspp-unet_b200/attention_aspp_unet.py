@@ -175,6 +175,7 @@ class AttentionASPPUNet(nn.Module):
         self._handle_device = None
         self._weights_version = None
         self._workspaces: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._last_ws = None
 
     # ---- engine lifetime -------------------------------------------------------------------------------
     def _config(self) -> _capi.AauConfig:
@@ -281,6 +282,7 @@ class AttentionASPPUNet(nn.Module):
         L = _capi.lib()
         with torch.cuda.device(x.device):
             ws = self._workspace(B, H, W, x.device)
+            self._last_ws = ws                                       # debug_tensor reads the workspace of the LAST forward
             ws_ptr = (ws.data_ptr() + 255) & ~255
             if out is not None:
                 if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * H * W or out.device != x.device:
@@ -352,7 +354,7 @@ class AttentionASPPUNet(nn.Module):
         v = [C.c_int() for _ in range(6)]
         _capi.check(self._handle, L.aau_debug_tensor(self._handle, name.encode(), C.byref(ptr), *[C.byref(i) for i in v]), "debug_tensor")
         B, H, W, Cc, ld, choff = [i.value for i in v]
-        ws = next(reversed(self._workspaces.values()))
+        ws = self._last_ws
         off = ptr.value - ws.data_ptr()
         dt = torch.bfloat16 if self.act_dtype == "bf16" else torch.float16
         flat = ws[off: off + B * H * W * ld * 2].view(dt).view(B, H, W, ld)

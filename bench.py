@@ -393,9 +393,11 @@ def run_engine(args):
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    picked = []
     for res in seg.segment_sweeps([vol_pinned] * args.steps, prob_thr=thr):
-        if world > 1:
-            gather_areas(np.array([res["best_area"], res["best_idx"]], np.int32), 2 * world, dev)   # host gather of per-case scores
+        picked += [res["best_area"], res["best_idx"]]
+    if world > 1:                                               # the only exchange: ONE host gather of the per-case scores of all ranks
+        gather_areas(np.array(picked, np.int32), len(picked) * world, dev)
     e1.record()
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))   # host work after the last kernel counts too

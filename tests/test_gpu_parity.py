@@ -347,6 +347,7 @@ def test_sweep_engine_matches_oracle_selection():
 # them per layer by shape, so each is forced here on shapes small enough for the oracle (fp16 storage: tight bound).
 OPTION_SETS = [
     {"rs": 0},                      # dx-stacked (AMODE_DXN) instead of row-shifted taps
+    {"rs": 2},                      # row-shifted taps for u1.conv.1 + out_conv too (dx-stacked by default since round 2)
     {"rs": 0, "amode": 1},          # column-shifted slabs for every 3x3 layer
     {"amode": 0},                   # one TMA box per tap
     {"rs_mt": 2},                   # 256-pixel row-shifted tiles everywhere

@@ -1,6 +1,6 @@
 """BASELINE.json configs[3]: the test_ablation variants (full / no attention gates / no ASPP / neither / att_depth 3) on
 562x744 frames, base_c=32: frames/s of the forward at batch 28 and parity of logits + psi maps against the oracle on one
-frame (fp16 storage for the parity leg, bf16 for the timing leg).
+frame (both storage types: parity and timing).
     python tools/ablation_bench.py [out.json]"""
 import json, sys
 from pathlib import Path
@@ -34,7 +34,7 @@ for name, kw, gflop in variants:
         rec[f"{dt}_logits_max_err"], rec[f"{dt}_logits_mean_err"] = float(err.max()), float(err.mean())
         rec[f"{dt}_mask_agreement_0.5"] = float(((lg.cpu() > 0) == (ref_logits > 0)).float().mean())
         rec[f"{dt}_psi_max_err"] = [float((a.cpu() - b).abs().max()) if a.numel() > 1 else 0.0 for a, b in zip(psis, ref_psis)]
-        if dt == "bf16":
+        if True:                                                # both storage types are timed (fp16 is the headline since round 2)
             xb = torch.from_numpy(vol).cuda()
             out = torch.empty((B, 1, H, W), dtype=torch.float32, device="cuda")
             for _ in range(3):
@@ -47,7 +47,7 @@ for name, kw, gflop in variants:
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            rec.update(ms_per_forward=ms, frames_per_s=1e3 * B / ms, tflops=B * gflop / ms, launches=net.num_launches())
+            rec.update({f"{dt}_ms_per_forward": ms, f"{dt}_frames_per_s": 1e3 * B / ms, f"{dt}_tflops": B * gflop / ms, "launches": net.num_launches()})
         net.check_device()
         del net
     rec["logit_std"] = float(ref_logits.std())
