@@ -55,6 +55,8 @@ SYMBOLS = [
     ("aau_tail_masks", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aau_condition_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int]),
     ("aau_condition_frames", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("aau_logit_cutoff", C.c_float, [C.c_float]),
+    ("aau_round_window_keep_sum", C.c_int, [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint16)]),
     ("aau_device_fault", C.c_int, [C.c_void_p]),
     ("aau_num_launches", C.c_int, [C.c_void_p]),
     ("aau_num_ops", C.c_int, [C.c_void_p]),

@@ -1798,6 +1798,15 @@ int aau_device_fault(aau_handle* h) {
     return AAU_OK;
 }
 
+// ---- host-only helpers of the weight preparation / selection head, exported so that they can be tested without a GPU
+float aau_logit_cutoff(float prob_thr) { return logit_cutoff(prob_thr); }
+
+int aau_round_window_keep_sum(const double* window9, int fp16, uint16_t* out9) {
+    if (!window9 || !out9) return AAU_ERR_INVALID;
+    round_window_keep_sum(window9, out9, fp16 != 0);
+    return AAU_OK;
+}
+
 int aau_num_launches(const aau_handle* h) { return h ? h->e.last_launches : 0; }
 int aau_last_forward_was_graph(const aau_handle* h) { return h ? h->e.last_replayed : 0; }
 int aau_num_ops(const aau_handle* h) { return (h && h->e.last_plan) ? (int)h->e.last_plan->ops.size() : 0; }

@@ -152,6 +152,15 @@ size_t aau_condition_workspace_bytes(const aau_handle* h, int N);
 int aau_condition_frames(aau_handle* h, const uint8_t* frames, int N, int H, int W, uint8_t* out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Host-only helpers (no device needed), exported for tests and for callers that prepare thresholds / weights themselves:
+ *   aau_logit_cutoff: the largest fp32 x with sigmoid(x) <= prob_thr for a correctly rounded fp32 sigmoid -- what
+ *     aau_frame_scores(AAU_IN_LOGITS) compares logits against (+inf for prob_thr >= 1, -inf for prob_thr < 0);
+ *   aau_round_window_keep_sum: the rounding aau_commit_weights applies to the nine BN-folded taps of one (out, in) channel pair
+ *     of a 3x3 convolution: nearest 16-bit values (fp16 != 0: IEEE half, else bfloat16 bit patterns), then single-ulp moves
+ *     until the rounded taps sum to within half an ulp of the true window sum (every tap stays within one ulp of its value). */
+float aau_logit_cutoff(float prob_thr);
+int aau_round_window_keep_sum(const double* window9, int fp16, uint16_t* out9);
+
 /* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
  * the device. */
 int aau_device_fault(aau_handle* h);

@@ -197,3 +197,55 @@ def test_two_rank_gather_gloo():
     full[[5, 11]] = 99
     for _, got, sel in res:
         assert got == full.tolist() and tuple(sel) == (5, 99)
+
+
+# ------------------------------------------------------------------------------------------------ host-only helpers of libaau
+def _lib():
+    import _capi
+    if not _capi.LIB_PATH.exists():
+        import __graft_entry__ as g
+        g.build()
+    return _capi.lib()
+
+
+def test_logit_cutoff_is_the_threshold_in_logit_space():
+    """sigmoid(x) > t  <=>  x > cutoff(t) (SURVEY.md identity i7): the library's cutoff (correctly rounded fp32 sigmoid, found
+    by bisection in C++) and the Python layer's (bisection on THIS host's torch.sigmoid) separate the fp32 line exactly."""
+    from fetal_abdomen import logit_cutoff
+    L = _lib()
+    for t in (0.05, 0.48, 0.5, 0.9, 1e-3, 0.999):
+        c = float(L.aau_logit_cutoff(ctypes.c_float(t)))
+        up = float(np.nextafter(np.float32(c), np.float32(np.inf)))
+        sig = lambda x: np.float32(1.0 / (1.0 + np.exp(-np.float64(x))))   # noqa: E731  correctly rounded fp32 sigmoid
+        assert not (sig(c) > np.float32(t)) and sig(up) > np.float32(t), t
+        assert abs(c - np.log(t / (1 - t))) < 1e-5 * max(1.0, abs(c))
+        ct = logit_cutoff(t)                                              # torch's own sigmoid: the same cutoff up to a few ulps
+        assert abs(ct - c) <= max(8 * abs(float(np.spacing(np.float32(c)))), 1e-7), (t, c, ct)   # (near 0 the sigmoid is flat to 2^-25)
+        x = torch.tensor([ct, float(np.nextafter(np.float32(ct), np.float32(np.inf)))] * 32, dtype=torch.float32)
+        assert (torch.sigmoid(x) > np.float32(t)).tolist()[:2] == [False, True]
+    assert float(L.aau_logit_cutoff(ctypes.c_float(1.0))) == float("inf") and float(L.aau_logit_cutoff(ctypes.c_float(-0.1))) == float("-inf")
+    assert logit_cutoff(1.0) == float("inf") and logit_cutoff(-0.1) == float("-inf")
+
+
+@pytest.mark.parametrize("fp16", [1, 0])
+def test_window_sum_preserving_rounding(fp16):
+    """aau_round_window_keep_sum (what aau_commit_weights applies to every 3x3 window): each tap within one ulp of its value,
+    the rounded taps sum to within half an ulp (of the largest tap) of the true sum, never worse than plain nearest rounding."""
+    L = _lib()
+    rng = np.random.default_rng(5)
+    to_f = (lambda b: b.view(np.float16).astype(np.float64)) if fp16 else (lambda b: (b.astype(np.uint32) << 16).view(np.float32).astype(np.float64))
+    ulp = (lambda v: np.spacing(np.abs(v).astype(np.float16)).astype(np.float64)) if fp16 else (lambda v: np.abs(v) * 2.0 ** -7)
+    worse = better = 0
+    for _ in range(400):
+        w = rng.uniform(-1, 1, 9) * rng.choice([1e-3, 3e-2, 0.2, 1.0])
+        out = np.zeros(9, np.uint16)
+        assert L.aau_round_window_keep_sum(w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), fp16, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16))) == 0
+        r = to_f(out)
+        assert np.all(np.abs(r - w) <= 1.001 * ulp(w) + 1e-12)            # every weight stays within one ulp
+        nearest = w.astype(np.float16).astype(np.float64) if fp16 else to_f(((w.astype(np.float32).view(np.uint32) + 0x7FFF + ((w.astype(np.float32).view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16))
+        e_keep, e_near = abs(r.sum() - w.sum()), abs(nearest.sum() - w.sum())
+        assert e_keep <= 0.5001 * ulp(w).max() + 1e-12                    # the window sum is kept to half an ulp of the largest tap
+        assert e_keep <= e_near + 1e-12
+        worse += e_keep > e_near
+        better += e_keep < e_near
+    assert better > 200 and worse == 0
