@@ -249,4 +249,4 @@ def test_window_sum_preserving_rounding(fp16):
         assert e_keep <= e_near + 1e-12
         worse += e_keep > e_near
         better += e_keep < e_near
-    assert better > 200 and worse == 0
+    assert better > 100 and worse == 0                                  # (equal whenever nearest rounding already keeps the sum)
