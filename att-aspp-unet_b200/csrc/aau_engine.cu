@@ -146,6 +146,7 @@ struct Engine {
     int opt_spec = 1;         // use the igemm instantiations specialised per (staging mode, epilogue) where they exist
     int opt_pair = 7;         // CTA pairs (cta_group::2): bit 0 slab-staged layers, bit 1 per-tap staged layers, bit 2 resident-weight small-N
                               // layers, bit 3 resident-weight transposed convs (HBM-bound: measured neutral, off by default)
+    int opt_fixcompact = 1;   // CONVTFIX keeps / multiplies only the non-zero weight blocks
     int opt_tapskip = 1;      // per-tap staged 3x3 layers skip taps whose box lies outside the image (igemm_tc.cuh: tap_outside)
     int opt_aspp_merge = 0;   // (measured slower: 0.81 vs 0.69 ms, tools/layer_ab.py) ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 with dilation > image
     int opt_keep_sum = 1;     // 3x3 weights rounded with the window-sum-preserving rule (weight-preparation option: takes effect at commit)
@@ -843,7 +844,9 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     // resident weights need one N tile per CTA: either a single N tile, or (dx-stacked) a grid that is a multiple of
     // n_tiles so that the static striding keeps every CTA on the same N tile
     const bool can_res = descs.size() == 1 && (Ntot == n_out || dxn || cfix) && e.opt_resident != 0 && (!pair || pair_res);
-    const int res_bytes = (steps * P.b_slot_bytes + 1023) & ~1023;
+    // transposed conv + fix-up: only the non-zero blocks of the [up | mid0 | mid1] x (tap -1, tap 0) tile stay resident
+    const bool fix_compact = cfix && e.opt_fixcompact != 0 && !pair;
+    const int res_bytes = fix_compact ? ((nchunk * 3 * d0.fix_cc * swz + 1023) & ~1023) : ((steps * P.b_slot_bytes + 1023) & ~1023);
     auto cols_for = [&](int stages) { int c = 32; while (c < stages * BN * P.MT) c <<= 1; return c; };
     int ctas = (BN <= 128 && (!pair || pair_res)) ? 2 : 1;                      // measured: 2 CTAs co-reside, a third only queues
     ctas = std::min(ctas, 512 / cols_for(2));
@@ -897,7 +900,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     if (!ok) return e.fail(AAU_ERR_INVALID, "pipeline does not fit in shared memory");
     P.acc_stages = ng;                                            // epilogue group g drains accumulator stage g
     P.tmem_cols = cols_for(ng);
-    const int b_region = ((P.nB * P.b_slot_bytes) + 1023) & ~1023;
+    const int b_region = (fix_compact && P.b_resident) ? res_bytes : (((P.nB * P.b_slot_bytes) + 1023) & ~1023);
+    P.fix_compact = (fix_compact && P.b_resident) ? 1 : 0;
     P.b_region_bytes = b_region;
     P.is_fp16 = e.is_fp16() ? 1 : 0;
     P.tile_iter = e.opt_titer;
@@ -920,7 +924,7 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation tensor");
         const uint64_t bdims[2] = {(uint64_t)(dxn ? 3 * Cin : d.w->K), (uint64_t)(dxn ? 3 * d.w->N : d.w->N)};
         const uint64_t bstr[1] = {bdims[0] * 2};
-        const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)(pair ? BN / 2 : BN)};
+        const uint32_t bbox[2] = {(uint32_t)P.KC, (uint32_t)(P.fix_compact ? d0.fix_cc : (pair ? BN / 2 : BN))};
         if (!encode_map(e, &q.tmB, dxn ? (dxn_full ? d.w->dBdx_full : d.w->dBdx) : d.w->dB, 2, bdims, bstr, bbox, swz))
             return e.fail(AAU_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight tensor");
         q.bias = d.bias_img ? d.bias_img : d.w->dbias;
@@ -1877,7 +1881,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
         {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"tb", &e.opt_tb}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
-        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}, {"tapskip", &e.opt_tapskip}, {"aspp_merge", &e.opt_aspp_merge}};
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}, {"tapskip", &e.opt_tapskip}, {"fixcompact", &e.opt_fixcompact}, {"aspp_merge", &e.opt_aspp_merge}};
     for (const auto& o : plan_options) {
         if (n == o.first) {
             *o.second = value;

@@ -168,6 +168,7 @@ struct alignas(64) IgemmParams {
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int pair_order;         // CTA pairs over several N tiles: consecutive tiles are two M tiles of one N tile
     int TB;                 // images per tile (per-tap staging of small images: the TMA boxes span TB frames of TH rows each)
+    int fix_compact;        // CONVTFIX with resident weights: only the non-zero blocks are kept / multiplied (tap -1: `up`, tap 0: `mid0 | mid1`)
     int skip_oob;           // per-tap staging, 3x3: taps whose whole box lies outside the image (dilated ASPP branches) are not issued
     int* err;
 };
@@ -323,6 +324,13 @@ __device__ __forceinline__ void pool_staged_tile(uint32_t cs, uint32_t ps, int t
             uint32_t o2 = o0 + (uint32_t)(vw * c_pitch), o3 = o2 + (uint32_t)c_pitch;
             o0 ^= ((o0 >> 7) & swz_mask) << 4; o1 ^= ((o1 >> 7) & swz_mask) << 4;
             o2 ^= ((o2 >> 7) & swz_mask) << 4; o3 ^= ((o3 >> 7) & swz_mask) << 4;
+            if (c_pitch == 64 && (i & 1)) {
+                // 64-byte pixels: the left pixel of every 2x2 window sits in banks 0-15, the right one in banks 16-31, and the
+                // 8 threads of a quarter-warp cover two windows -- odd windows read right-then-left so that each LDS.128 spreads
+                // over all 32 banks instead of queueing two-deep on 16 (ncu: 2x excessive wavefronts on d1.1's four pool loads)
+                uint32_t t = o0; o0 = o1; o1 = t;
+                t = o2; o2 = o3; o3 = t;
+            }
             const uint4 m = max8(max8(lds128(cs + o0), lds128(cs + o1), f16), max8(lds128(cs + o2), lds128(cs + o3), f16), f16);
             uint32_t po = (uint32_t)((py * PW + px) * c_pitch + v * 16);
             po ^= ((po >> 7) & swz_mask) << 4;
@@ -424,6 +432,19 @@ __device__ __forceinline__ void mma_role(const IgemmParams& P, uint8_t* smem_a, 
                 const int bslot = res ? s : ib;
                 if (!res) ptx::mbar_wait(full_b + 8u * (uint32_t)ib, pb, P.err, ERR_MMA_WAIT_FULL);
                 ptx::tc_fence_after();
+                if (P.fix_compact) {                                          // CONVTFIX: tap -1 feeds `up` only, tap 0 feeds `mid0 | mid1`
+                    if (ptx::elect_one()) {
+                        const int CC = P.BN / 3, tap = s >= q.nchunk ? 1 : 0, ch = s - tap * q.nchunk;
+                        const uint32_t up16 = (uint32_t)(CC * swz) >> 4;
+                        const uint32_t b_lo = b_base + (tap ? (uint32_t)q.nchunk * up16 + (uint32_t)ch * 2u * up16 : (uint32_t)ch * up16);
+                        mma_subblock<KK, PAIR>(d_tmem + (tap ? (uint32_t)CC : 0u), a_base + ia * a_slot16, b_lo, desc_hi,
+                                               ptx::make_idesc_f16(128, tap ? 2 * CC : CC, P.is_fp16 != 0), ch == 0 ? 0u : 1u);
+                        ptx::umma_commit(empty_a + 8u * (uint32_t)ia);
+                    }
+                    __syncwarp();
+                    if (++ia == P.nA) { ia = 0; pa ^= 1; }
+                    continue;
+                }
                 if (ptx::elect_one()) {
                     mma_subblock<KK, PAIR>(d_tmem, a_base + ia * a_slot16, b_base + bslot * b_slot16, desc_hi, idesc, accumulate);
                     if (PAIR) { ptx::umma_commit_pair(empty_a + 8u * (uint32_t)ia); if (!res) ptx::umma_commit_pair(empty_b + 8u * (uint32_t)ib); }
@@ -596,7 +617,22 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 const IgemmProblem& q = P.prob[0];
                 const int cin = q.nchunk * P.KC;
                 const int steps = (amode == AMODE_DXN ? 3 : q.taps) * q.nchunk;
-                if (ptx::elect_one()) {
+                if (P.fix_compact) {
+                    // transposed conv + fix-up: of the [up | mid0 | mid1] x (tap -1, tap 0) weight tile only `up` x tap -1 and
+                    // `mid0 | mid1` x tap 0 are non-zero (prep_upfix): the tap -1 sub-blocks keep CC rows, the tap 0 ones 2 CC
+                    // (half the shared memory of the padded tile -- it goes to the A ring -- and 42 % fewer MMA cycles)
+                    if (ptx::elect_one()) {
+                        const int CC = P.BN / 3, n0 = (int)(blockIdx.x % q.n_tiles) * P.BN;
+                        const uint32_t up_bytes = (uint32_t)(CC * P.KC * 2);
+                        ptx::mbar_expect_tx(&b_res_bar, (uint32_t)q.nchunk * 3u * up_bytes);
+                        for (int ch = 0; ch < q.nchunk; ++ch) {
+                            ptx::tma_load_2d(smem_b + (size_t)ch * up_bytes, &q.tmB, &b_res_bar, ch * P.KC, n0);
+                            uint8_t* mid = smem_b + (size_t)q.nchunk * up_bytes + (size_t)ch * 2 * up_bytes;
+                            ptx::tma_load_2d(mid, &q.tmB, &b_res_bar, (q.nchunk + ch) * P.KC, n0 + CC);
+                            ptx::tma_load_2d(mid + up_bytes, &q.tmB, &b_res_bar, (q.nchunk + ch) * P.KC, n0 + 2 * CC);
+                        }
+                    }
+                } else if (ptx::elect_one()) {
                     // pair: each CTA keeps HALF of the weight rows of every sub-block; both halves complete the leader's barrier
                     if (!PAIR || pair_rank == 0) ptx::mbar_expect_tx(&b_res_bar, (uint32_t)((PAIR ? 2 : 1) * steps * P.b_slot_bytes));
                     for (int s = 0; s < steps; ++s) {

@@ -194,6 +194,7 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *              (both re-run the weight preparation: they synchronise the device)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
  *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
+ *   "fixcompact" 1/0 the fused transposed-conv + fix-up GEMM keeps and multiplies only the non-zero blocks of its weight tile
  *   "tapskip"  1/0 per-tap staged 3x3 layers (the dilated ASPP branches) skip taps whose whole box lies outside the image
  *   "aspp_merge" 1/0 ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 (needs "tapskip")
  *   "graph"    CUDA-graph replay of the forward's launch sequence: -1 auto (batches of at most "graph_max_px" = B*H*W pixels,

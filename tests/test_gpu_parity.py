@@ -405,6 +405,10 @@ def test_fused_transposed_conv_and_bilinear_fixup(c, shape):
     net.set_option("fusefix", 0)
     split = net(x.cuda()).cpu()
     assert not any("up+resize" in r["layer"] for r in net.op_profile())
+    net.set_option("fusefix", 1)
+    net.set_option("fixcompact", 0)                                    # the padded weight tile (structural zeros multiplied): same sums
+    padded = net(x.cuda()).cpu()
+    assert (padded - fused).abs().max().item() <= 1e-6 * max(1.0, fused.abs().max().item())
     net.check_device()
     spread = ref.std().item()
     e_f, e_s = (fused - ref).abs(), (split - ref).abs()
