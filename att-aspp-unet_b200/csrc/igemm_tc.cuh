@@ -798,6 +798,13 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 sb0[i] = __ldg(q0.bias + (EPI_OF(q0) == EPI_CONVT ? (n0 + i) % q0.convt_cout
                                           : EPI_OF(q0) == EPI_CONVTFIX ? ((n0 / P.BN) * (P.BN / 3) + i % (P.BN / 3)) % q0.convt_cout : n0 + i));
         }
+        // 32-channel STORE layers with a static bias (d1.1 -- the largest layer of the forward): the 32 bias values live in
+        // registers for the whole kernel instead of eight LDS.128 per tile in front of the first FADD of the conversion chain
+        // (ncu source view of d1.1: 13 % of the kernel's samples were FADDs waiting on those loads, short_sb)
+        const bool bias_regs = bias_static && P.BN == 32 && P.CB == 32 && P.n_out == 32 && amode != AMODE_DXN && EPI_OF(P.prob[0]) == EPI_STORE;
+        float4 bq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bq[k] = bias_regs ? __ldg(reinterpret_cast<const float4*>(P.prob[0].bias) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         // The barrier at the top of a tile publishes the tile's bias and the "staging tile is free again" news.  With a
         // static bias it can go when nothing is staged (OUTCONV), or when tiles are single-chunk STOREs alternating
         // between two staging tiles: there thread 0 waits for the PREVIOUS tile's store to have read its tile right
@@ -955,9 +962,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         const uint32_t xr = ((row_base >> 7) & swz_mask) << 4;
                         const uint32_t cs_row = cs + row_base;
                         const bool relu = q.relu != 0;
-                        auto convert8 = [&](const uint32_t* r8, int col) {           // 8 accumulator columns -> one 16-byte vector
-                            const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + col);
-                            const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + col + 4);
+                        auto convert8b = [&](const uint32_t* r8, int col, const float4& b0, const float4& b1) {   // 8 accumulator columns -> one 16-byte vector
                             const float f0 = __uint_as_float(r8[0]) + b0.x, f1 = __uint_as_float(r8[1]) + b0.y;
                             const float f2 = __uint_as_float(r8[2]) + b0.z, f3 = __uint_as_float(r8[3]) + b0.w;
                             const float f4 = __uint_as_float(r8[4]) + b1.x, f5 = __uint_as_float(r8[5]) + b1.y;
@@ -966,7 +971,20 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                                  : make_uint4(pack2(f0, f1, f16), pack2(f2, f3, f16), pack2(f4, f5, f16), pack2(f6, f7, f16));
                             if (colok) sts128(cs_row + ((uint32_t)(col * 2) ^ xr), o);
                         };
-                        if ((P.CB & 31) == 0) {
+                        auto convert8 = [&](const uint32_t* r8, int col) {
+                            convert8b(r8, col, *reinterpret_cast<const float4*>(sb + c0 + col), *reinterpret_cast<const float4*>(sb + c0 + col + 4));
+                        };
+                        if (bias_regs) {                                             // BN == CB == 32: one pass, bias from registers
+                            uint32_t ra[32], rb[32];
+                            ptx::tmem_ld_32x16(taddr, ra);
+                            ptx::tmem_ld_wait();
+                            ptx::tmem_ld_32x16(taddr + 16, rb);
+                            convert8b(ra, 0, bq[0], bq[1]);
+                            convert8b(ra + 8, 8, bq[2], bq[3]);
+                            ptx::tmem_ld_wait();
+                            convert8b(rb, 16, bq[4], bq[5]);
+                            convert8b(rb + 8, 24, bq[6], bq[7]);
+                        } else if ((P.CB & 31) == 0) {
                             // 16 accumulator columns at a time, the next 16 in flight while these are converted (one x32
                             // load per 32 columns left the whole TMEM read latency in front of the first FADD: 21 % of
                             // d1.1's epilogue samples)
