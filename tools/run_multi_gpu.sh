@@ -1,3 +1,4 @@
+# bash tools/run_multi_gpu.sh N  (on a box with N GPUs): frame-sharded single sweep, weak-scaling bench and the CPU reference arm under torchrun
 set -x
 N=$1
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --split sweep --steps 5 --warmup 2 > gpurun_out/r02_split_sweep_${N}gpu.json 2> gpurun_out/r02_split_sweep_${N}gpu.err
