@@ -801,10 +801,15 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
         // 32-channel STORE layers with a static bias (d1.1 -- the largest layer of the forward): the 32 bias values live in
         // registers for the whole kernel instead of eight LDS.128 per tile in front of the first FADD of the conversion chain
         // (ncu source view of d1.1: 13 % of the kernel's samples were FADDs waiting on those loads, short_sb)
-        const bool bias_regs = bias_static && P.BN == 32 && P.CB == 32 && P.n_out == 32 && amode != AMODE_DXN && EPI_OF(P.prob[0]) == EPI_STORE;
-        float4 bq[8];
+        // (only in the instantiation that layer uses -- row-shifted taps, STORE, KC = 32: elsewhere the 32 registers would be
+        // reserved for nothing and push the conversion loop into spills)
+        constexpr bool BIAS_REGS = (AM == AMODE_RS && EP == EPI_STORE && KKT == 2);
+        const bool bias_regs = BIAS_REGS && bias_static && P.BN == 32 && P.CB == 32 && P.n_out == 32;
+        float4 bq[BIAS_REGS ? 8 : 1];
+        if constexpr (BIAS_REGS) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bq[k] = bias_regs ? __ldg(reinterpret_cast<const float4*>(P.prob[0].bias) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 8; ++k) bq[k] = bias_regs ? __ldg(reinterpret_cast<const float4*>(P.prob[0].bias) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         // The barrier at the top of a tile publishes the tile's bias and the "staging tile is free again" news.  With a
         // static bias it can go when nothing is staged (OUTCONV), or when tiles are single-chunk STOREs alternating
         // between two staging tiles: there thread 0 waits for the PREVIOUS tile's store to have read its tile right
@@ -974,31 +979,42 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         auto convert8 = [&](const uint32_t* r8, int col) {
                             convert8b(r8, col, *reinterpret_cast<const float4*>(sb + c0 + col), *reinterpret_cast<const float4*>(sb + c0 + col + 4));
                         };
-                        if (bias_regs) {                                             // BN == CB == 32: one pass, bias from registers
-                            uint32_t ra[32], rb[32];
-                            ptx::tmem_ld_32x16(taddr, ra);
-                            ptx::tmem_ld_wait();
-                            ptx::tmem_ld_32x16(taddr + 16, rb);
-                            convert8b(ra, 0, bq[0], bq[1]);
-                            convert8b(ra + 8, 8, bq[2], bq[3]);
-                            ptx::tmem_ld_wait();
-                            convert8b(rb, 16, bq[4], bq[5]);
-                            convert8b(rb + 8, 24, bq[6], bq[7]);
+                        bool done = false;
+                        if constexpr (BIAS_REGS) {
+                            if (bias_regs) {                                         // BN == CB == 32: one pass, bias from registers
+                                uint32_t ra[32], rb[32];
+                                ptx::tmem_ld_32x16(taddr, ra);
+                                ptx::tmem_ld_wait();
+                                ptx::tmem_ld_32x16(taddr + 16, rb);
+                                convert8b(ra, 0, bq[0], bq[1]);
+                                convert8b(ra + 8, 8, bq[2], bq[3]);
+                                ptx::tmem_ld_wait();
+                                convert8b(rb, 16, bq[4], bq[5]);
+                                convert8b(rb + 8, 24, bq[6], bq[7]);
+                                done = true;
+                            }
+                        }
+                        if (done) {
                         } else if ((P.CB & 31) == 0) {
                             // 16 accumulator columns at a time, the next 16 in flight while these are converted (one x32
                             // load per 32 columns left the whole TMEM read latency in front of the first FADD: 21 % of
                             // d1.1's epilogue samples)
+                            // (the bias vectors of each 16-column step are read BEFORE the wait on that step's accumulator load,
+                            // so their shared-memory latency hides under it instead of stalling the first FADDs)
                             uint32_t ra[32], rb[32];
                             ptx::tmem_ld_32x16(taddr + c0, ra);
                             for (int cc = 0; cc < P.CB; cc += 32) {
+                                const float4* bp = reinterpret_cast<const float4*>(sb + c0 + cc);
+                                const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
                                 ptx::tmem_ld_wait();
                                 ptx::tmem_ld_32x16(taddr + c0 + cc + 16, rb);
-                                convert8(ra, cc);
-                                convert8(ra + 8, cc + 8);
+                                const float4 b4 = bp[4], b5 = bp[5], b6 = bp[6], b7 = bp[7];
+                                convert8b(ra, cc, b0, b1);
+                                convert8b(ra + 8, cc + 8, b2, b3);
                                 ptx::tmem_ld_wait();
                                 if (cc + 32 < P.CB) ptx::tmem_ld_32x16(taddr + c0 + cc + 32, ra);
-                                convert8(rb, cc + 16);
-                                convert8(rb + 8, cc + 24);
+                                convert8b(rb, cc + 16, b4, b5);
+                                convert8b(rb + 8, cc + 24, b6, b7);
                             }
                         } else {                                                     // CB == 16
                             uint32_t r[32];
