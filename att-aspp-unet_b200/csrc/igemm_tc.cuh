@@ -876,11 +876,14 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     ptx::tmem_ld_32x16(taddr + c0, e0);
                     ptx::tmem_ld_32x16(taddr + N + c0, e1);
                     ptx::tmem_ld_32x16(taddr + 2 * N + c0, e2);
+                    float4 bq4[4];                                              // bias read under the accumulator loads
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) bq4[v] = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
                     ptx::tmem_ld_wait();
                     float f[16];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
+                        const float4 b4 = bq4[v];
                         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -1093,6 +1096,12 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         ptx::tmem_ld_32x16(taddr + c0 + cc, u);
                         ptx::tmem_ld_32x16(taddr + CC + c0 + cc, m0);
                         ptx::tmem_ld_32x16(taddr + 2 * CC + c0 + cc, m1);
+                        float bsv[16];                                          // bias read under the accumulator loads
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 4);
+                            bsv[v * 4 + 0] = b4.x; bsv[v * 4 + 1] = b4.y; bsv[v * 4 + 2] = b4.z; bsv[v * 4 + 3] = b4.w;
+                        }
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int p = 0; p < 2; ++p) {
@@ -1103,7 +1112,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                 for (int i = 0; i < 8; ++i) {
                                     const int c = v * 8 + i;
                                     f[i] = fmaf(cf[p][0], __uint_as_float(u[c]), fmaf(cf[p][1], __uint_as_float(m0[c]),
-                                                fmaf(cf[p][2], __uint_as_float(m1[c]), sb[c0 + cc + c])));
+                                                fmaf(cf[p][2], __uint_as_float(m1[c]), bsv[c])));
                                 }
                                 const uint4 o4 = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
                                 sts128(slot0 + (uint32_t)(p * P.c_slot_bytes) + row_base + ((uint32_t)((cc + v * 8) * 2) ^ xr), o4);
@@ -1133,11 +1142,16 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                 for (int c0 = 0; c0 < P.BN; c0 += 16) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x16(taddr + c0, r);
+                    float4 bb[4], ww[4];                                        // read under the accumulator load, not after it
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        bb[v] = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
+                        ww[v] = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
+                    }
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float4 b = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
-                        const float4 w = *reinterpret_cast<const float4*>(s_vec + c0 + v * 4);
+                        const float4 b = bb[v], w = ww[v];
                         dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 0]) + b.x, 0.f), w.x, dot);
                         dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 1]) + b.y, 0.f), w.y, dot);
                         dot = fmaf(fmaxf(__uint_as_float(r[v * 4 + 2]) + b.z, 0.f), w.z, dot);
