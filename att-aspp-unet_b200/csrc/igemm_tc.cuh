@@ -855,6 +855,12 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
             }
             TM_MARK(0);                                         // 0: tile bookkeeping
             if (etid == 0 && !skip_top_bar) WAIT_STORE_READS(); // the store that last used the next staging tile has left smem
+            if (EPI_OF(q) == EPI_GATE && etid == 0) {
+                // attention gate: the first chunk of the skip tile that psi will scale does not depend on the MMAs -- fetch it
+                // now, under the wait for the accumulator, instead of after the sigmoid
+                ptx::mbar_expect_tx(cbar, (uint32_t)P.c_slot_bytes);
+                ptx::tma_load_4d(cs, &P.tmC[0], cbar, 0, tc.x0, tc.y0, tc.b);
+            }
             TM_MARK(1);                                         // 1: wait for the previous TMA store to have read its tile
             ptx::mbar_wait(full_bar, acc_phase, P.err, ERR_EPI_WAIT);
             acc_phase ^= 1;
@@ -876,14 +882,11 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     ptx::tmem_ld_32x16(taddr + c0, e0);
                     ptx::tmem_ld_32x16(taddr + N + c0, e1);
                     ptx::tmem_ld_32x16(taddr + 2 * N + c0, e2);
-                    float4 bq4[4];                                              // bias read under the accumulator loads
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) bq4[v] = *reinterpret_cast<const float4*>(sb + c0 + v * 4);
                     ptx::tmem_ld_wait();
                     float f[16];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float4 b4 = bq4[v];
+                        const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + v * 4);   // (hoisting these above the wait measured +1.7 % on u1.conv.1)
                         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -1096,12 +1099,6 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                         ptx::tmem_ld_32x16(taddr + c0 + cc, u);
                         ptx::tmem_ld_32x16(taddr + CC + c0 + cc, m0);
                         ptx::tmem_ld_32x16(taddr + 2 * CC + c0 + cc, m1);
-                        float bsv[16];                                          // bias read under the accumulator loads
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + cc + v * 4);
-                            bsv[v * 4 + 0] = b4.x; bsv[v * 4 + 1] = b4.y; bsv[v * 4 + 2] = b4.z; bsv[v * 4 + 3] = b4.w;
-                        }
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int p = 0; p < 2; ++p) {
@@ -1112,7 +1109,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                                 for (int i = 0; i < 8; ++i) {
                                     const int c = v * 8 + i;
                                     f[i] = fmaf(cf[p][0], __uint_as_float(u[c]), fmaf(cf[p][1], __uint_as_float(m0[c]),
-                                                fmaf(cf[p][2], __uint_as_float(m1[c]), bsv[c])));
+                                                fmaf(cf[p][2], __uint_as_float(m1[c]), sb[c0 + cc + c])));
                                 }
                                 const uint4 o4 = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16), pack2(f[6], f[7], f16));
                                 sts128(slot0 + (uint32_t)(p * P.c_slot_bytes) + row_base + ((uint32_t)((cc + v * 8) * 2) ^ xr), o4);
@@ -1170,7 +1167,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
                     // scale the skip tile in place: TMA load (L2 hit: the same bytes were just streamed in as the A
                     // operand) -> multiply this thread's pixel row in shared memory -> TMA store, CB channels at a time
                     for (int c0 = 0; c0 < q.gate_C; c0 += P.CB) {
-                        if (etid == 0) {
+                        if (etid == 0 && c0 > 0) {                          // (chunk 0 was requested at the top of the tile)
                             WAIT_STORE_READS();
                             ptx::mbar_expect_tx(cbar, (uint32_t)P.c_slot_bytes);
                             ptx::tma_load_4d(cs, &P.tmC[0], cbar, c0, tc.x0, tc.y0, tc.b);
