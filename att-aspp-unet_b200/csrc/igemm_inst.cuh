@@ -39,7 +39,7 @@ bool igemm_spec_fp16_raise(int bytes);
 }  // namespace aau
 
 // body of one table translation unit
-#define AAU_IGEMM_DEFINE_TABLE(LIST, F, LOOKUP_NAME, RAISE_NAME, GENERIC)                                                             \
+#define AAU_IGEMM_DEFINE_TABLE(LIST, F, RAISE_NAME)                                                            \
     namespace aau {                                                                                                                   \
     static const void* table_lookup(int ng, bool multi, bool pair, int am, int ep, int kk, int pl) {                                  \
         LIST(AAU_IGEMM_X_LOOKUP, F)                                                                                                   \

@@ -45,9 +45,9 @@
 // two SMs.  Launches with several N tiles walk the tiles pairwise (`pair_order`) so that a pair shares its N tile.
 //
 // Instantiations: the template parameters AM / EP / KKT / PL fix the staging mode, the epilogue, the MMAs per sub-block
-// and the fused MaxPool at compile time for the bf16 hot path (a third of the generic kernel's 110 KB of SASS: the
+// and the fused MaxPool at compile time for the hot path, both storage types (a third of the generic kernel's 110 KB of SASS: the
 // single-warp roles miss the instruction cache less and skip the uniform mode branches); -1 = decided at run time
-// from IgemmParams, which every plan, fp16 storage and the forced-plan parity tests can use.
+// from IgemmParams, which every plan and the forced-plan parity tests can use (igemm_inst.cuh lists the instantiations).
 //
 // Warp roles (64 + 128*NG threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run warp-uniform,
 // the asynchronous instructions under elect.sync), then NG in {2, 4} epilogue groups of four warps (one warp per TMEM
