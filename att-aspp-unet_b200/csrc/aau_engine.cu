@@ -106,6 +106,7 @@ struct Plan {
     float *g_logits = nullptr, *g_psi3 = nullptr, *g_psi2 = nullptr;
     cudaGraphExec_t g_exec[2] = {nullptr, nullptr};   // by x_dtype
     bool g_failed = false;
+    int fault_armed = 0;                 // fault injection: one launch per plan
     ~Plan() {
         for (cudaEvent_t ev : events) cudaEventDestroy(ev);
         for (cudaGraphExec_t g : g_exec)
@@ -131,6 +132,8 @@ struct Engine {
     float cut_thr = NAN, cut_val = 0.f;                // last (probability threshold -> logit cutoff) pair
     std::vector<std::unique_ptr<Plan>> plans;
     int* d_err = nullptr;
+    int* h_err = nullptr;                             // mapped pinned copy of the fault code: readable after a trapped kernel
+    int opt_fault_inject = 0;                         // tests: the first tensor-core launch of a plan gets a silent TMA producer
     cudaStream_t side_stream = nullptr;               // ASPP image-pooling branch (fork / join around the conv branches)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t graph_stream = nullptr;              // graph replays run here (a legacy default stream cannot be captured)
@@ -908,6 +911,8 @@ static int add_igemm(Engine& e, Plan& plan, const std::string& name, const std::
     P.skip_oob = (e.opt_tapskip != 0 && P.amode == AMODE_TAP && d0.w->taps == 9) ? 1 : 0;
     P.lean_sync = e.opt_lean;
     P.err = e.d_err;
+    P.fault_inject = (e.opt_fault_inject != 0 && plan.fault_armed == 0) ? 1 : 0;
+    if (P.fault_inject) plan.fault_armed = 1;
     P.nprob = (int)descs.size();
     int tile_begin = 0;
     for (int i = 0; i < P.nprob; ++i) {
@@ -1412,6 +1417,16 @@ int aau_create(const aau_config* cfg, int device, aau_handle** out) {
         delete h;
         return AAU_ERR_CUDA;
     }
+    {   // the fault code also lands in mapped pinned memory (device pointer stored at d_err + 2 ints): a trapped context cannot be read back
+        int* dev_view = nullptr;
+        if (cudaHostAlloc((void**)&e.h_err, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer((void**)&dev_view, e.h_err, 0) == cudaSuccess) {
+            memset(e.h_err, 0, 64);
+            cudaMemcpy((char*)e.d_err + 8, &dev_view, sizeof(dev_view), cudaMemcpyHostToDevice);
+        } else {
+            cudaGetLastError();
+            e.h_err = nullptr;                                        // diagnostics only: the device flag still works while the context lives
+        }
+    }
     if (cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -1445,6 +1460,7 @@ int aau_destroy(aau_handle* h) {
     cudaSetDevice(h->e.device);
     for (void* p : h->e.dev_allocs) cudaFree(p);
     if (h->e.d_err) cudaFree(h->e.d_err);
+    if (h->e.h_err) cudaFreeHost(h->e.h_err);
     if (h->e.side_stream) cudaStreamDestroy(h->e.side_stream);
     if (h->e.ev_fork) cudaEventDestroy(h->e.ev_fork);
     if (h->e.ev_join) cudaEventDestroy(h->e.ev_join);
@@ -1789,16 +1805,34 @@ int aau_best_frame(aau_handle* h, const int32_t* areas, int N, int32_t* best, vo
     return AAU_OK;
 }
 
+static const char* fault_name(int code) {
+    switch (code) {
+        case ERR_PRODUCER_WAIT: return "TMA producer waiting for a free ring slot";
+        case ERR_MMA_WAIT_FULL: return "MMA issuer waiting for operands";
+        case ERR_MMA_WAIT_TMEM: return "MMA issuer waiting for a free accumulator stage";
+        case ERR_EPI_WAIT: return "epilogue waiting for an accumulator / a skip tile";
+        case ERR_STEM_BUILD_WAIT: return "stem builders waiting";
+        case ERR_STEM_MMA_WAIT: return "stem MMA issuer waiting";
+        case ERR_STEM_EPI_WAIT: return "stem epilogue waiting";
+        default: return "unknown";
+    }
+}
+
 int aau_device_fault(aau_handle* h) {
     if (!h) return AAU_ERR_INVALID;
     Engine& e = h->e;
     cudaSetDevice(e.device);
     cudaError_t r = cudaDeviceSynchronize();
     int flag = 0;
-    cudaError_t r2 = cudaMemcpy(&flag, e.d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    if (r != cudaSuccess || r2 != cudaSuccess)
-        return e.fail(AAU_ERR_DEVICE, std::string("device error: ") + cudaGetErrorString(r != cudaSuccess ? r : r2) + " (pipeline flag " + std::to_string(flag) + ")");
-    if (flag) return e.fail(AAU_ERR_DEVICE, "kernel pipeline wait timed out, code " + std::to_string(flag));
+    cudaError_t r2 = r == cudaSuccess ? cudaMemcpy(&flag, e.d_err, sizeof(int), cudaMemcpyDeviceToHost) : r;
+    const int host_flag = e.h_err ? *reinterpret_cast<volatile int*>(e.h_err) : 0;   // survives a trapped context
+    if (!flag) flag = host_flag;
+    if (r != cudaSuccess || r2 != cudaSuccess) {
+        std::string msg = std::string("device error: ") + cudaGetErrorString(r != cudaSuccess ? r : r2);
+        if (flag) msg += std::string("; kernel pipeline wait timed out, code ") + std::to_string(flag) + " (" + fault_name(flag) + ")";
+        return e.fail(AAU_ERR_DEVICE, msg);
+    }
+    if (flag) return e.fail(AAU_ERR_DEVICE, "kernel pipeline wait timed out, code " + std::to_string(flag) + " (" + fault_name(flag) + ")");
     return AAU_OK;
 }
 
@@ -1881,7 +1915,7 @@ int aau_set_option(aau_handle* h, const char* name, int value) {
         {"amode", &e.opt_amode}, {"rs", &e.opt_rs}, {"rs_mt", &e.opt_rs_mt}, {"resident", &e.opt_resident}, {"ctas", &e.opt_ctas},
         {"ng", &e.opt_ng}, {"cslots", &e.opt_cslots}, {"mt", &e.opt_mt}, {"slab_max_bn", &e.opt_slab_max_bn},
         {"fusepool", &e.opt_fusepool}, {"fusefix", &e.opt_fusefix}, {"fixcc", &e.opt_fixcc}, {"convt_batch", &e.opt_convt_batch}, {"pair", &e.opt_pair}, {"spec", &e.opt_spec}, {"tb", &e.opt_tb}, {"stem_tc", &e.opt_stem_tc}, {"mt_shape", &e.opt_mt_shape}, {"dxn_full", &e.opt_dxn_full}, {"side", &e.opt_side},
-        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}, {"tapskip", &e.opt_tapskip}, {"fixcompact", &e.opt_fixcompact}, {"aspp_merge", &e.opt_aspp_merge}};
+        {"pdl", &e.opt_pdl}, {"titer", &e.opt_titer}, {"lean", &e.opt_lean}, {"graph", &e.opt_graph}, {"tapskip", &e.opt_tapskip}, {"fixcompact", &e.opt_fixcompact}, {"fault_inject", &e.opt_fault_inject}, {"aspp_merge", &e.opt_aspp_merge}};
     for (const auto& o : plan_options) {
         if (n == o.first) {
             *o.second = value;

@@ -168,6 +168,7 @@ struct alignas(64) IgemmParams {
     int tile_iter;          // 1: incremental tile coordinates (single-problem launches), 0: full decode per tile
     int pair_order;         // CTA pairs over several N tiles: consecutive tiles are two M tiles of one N tile
     int TB;                 // images per tile (per-tap staging of small images: the TMA boxes span TB frames of TH rows each)
+    int fault_inject;       // test hook: the TMA producer of CTA 0 never loads anything, so its MMA warp runs into the bounded wait
     int fix_compact;        // CONVTFIX with resident weights: only the non-zero blocks are kept / multiplied (tap -1: `up`, tap 0: `mid0 | mid1`)
     int skip_oob;           // per-tap staging, 3x3: taps whose whole box lies outside the image (dilated ASPP branches) are not issued
     int* err;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(igemm_threads(NG), NG == 2 ? 2 : 1) igemm_tc_k
     if (warp == 0) {
         // =========================== TMA producer ===========================
         // whole warp, warp-uniform control flow; the TMA instructions themselves are issued under elect.sync
-        {
+        if (!(P.fault_inject && blockIdx.x == 0)) {   // (fault injection, tests only: a silent producer must end in a reported trap, not a hang)
             int ia = 0, ib = 0;
             uint32_t pa = 0, pb = 0;
             const bool res = P.b_resident != 0;

@@ -47,11 +47,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must never hang the GPU box.  try_wait itself sleeps in hardware for a
 // bounded time per call, so ~2^22 failed probes is on the order of seconds.
+// The fault record: err_flag[0] on the device, and -- because a trapped context can no longer be read -- a copy in mapped
+// pinned host memory whose device pointer the engine stores at err_flag + 2 (aau_device_fault reads it after the trap).
+__device__ __forceinline__ void report_fault(int* err_flag, int code) {
+    if (!err_flag) return;
+    atomicExch(err_flag, code);
+    int* host = *reinterpret_cast<int* volatile*>(err_flag + 2);
+    if (host) {
+        *reinterpret_cast<volatile int*>(host) = code;
+        __threadfence_system();
+    }
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) {
-            if (err_flag) atomicExch(err_flag, code);
+            report_fault(err_flag, code);
             __trap();
         }
     }
@@ -84,7 +95,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) {
-            if (err_flag) atomicExch(err_flag, code);
+            report_fault(err_flag, code);
             __trap();
         }
     }

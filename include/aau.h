@@ -161,8 +161,10 @@ int aau_condition_frames(aau_handle* h, const uint8_t* frames, int N, int H, int
 float aau_logit_cutoff(float prob_thr);
 int aau_round_window_keep_sum(const double* window9, int fp16, uint16_t* out9);
 
-/* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Synchronises
- * the device. */
+/* Device-side fault flag raised by a kernel whose internal pipeline wait timed out (0 = none).  Every mbarrier wait in the
+ * kernels is bounded; on a timeout the kernel records a code (which role was waiting for what) and traps instead of hanging
+ * the GPU.  The code is also written to mapped pinned host memory, so it is reported even though the trapped context can no
+ * longer be read.  Synchronises the device. */
 int aau_device_fault(aau_handle* h);
 
 /* Debug / measurement aids. */
@@ -194,6 +196,9 @@ int aau_debug_tensor(aau_handle* h, const char* name, void** ptr, int* B, int* H
  *              (both re-run the weight preparation: they synchronise the device)
  *   "fusepool" "fusefix" "fixcc"   MaxPool2d / bilinear fix-up fused into the producing GEMM's epilogue
  *   "side" "pdl" "titer"   side stream for the ASPP pooling branch, programmatic dependent launch, incremental tile walk
+ *   "fault_inject" 1: TEST HOOK -- the first tensor-core launch of the next plan gets a silent TMA producer in CTA 0, so that its
+ *              MMA issuer runs into the bounded mbarrier wait: the kernel traps and aau_device_fault reports the code (the CUDA
+ *              context is lost afterwards: use a scratch process)
  *   "fixcompact" 1/0 the fused transposed-conv + fix-up GEMM keeps and multiplies only the non-zero blocks of its weight tile
  *   "tapskip"  1/0 per-tap staged 3x3 layers (the dilated ASPP branches) skip taps whose whole box lies outside the image
  *   "aspp_merge" 1/0 ASPP blocks.0 (1x1) rides in the dilated branches' launch as the centre tap of a 3x3 (needs "tapskip")

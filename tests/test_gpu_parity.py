@@ -433,3 +433,40 @@ def test_small_and_odd_shapes(c, shape):
     spread = ref.std().item()
     assert (out - ref).abs().max().item() <= 0.03 * spread + 2e-2
     assert agreement(out, ref, 0.5) >= 0.99
+
+
+# ------------------------------------------------------------------------------------------------ bounded waits
+def test_pipeline_fault_is_reported_not_hung():
+    """Every mbarrier wait in the kernels is bounded: a pipeline that stops feeding (here: an injected silent TMA producer) must end in
+    a trap whose code reaches the host -- through mapped pinned memory, the trapped context cannot be read -- and never in a hung
+    GPU.  Runs in a scratch process because the CUDA context does not survive the trap."""
+    import subprocess, sys, time
+    from conftest import ROOT
+    code = r"""
+import sys, time
+sys.path[:0] = [r'%s', r'%s']
+import torch, aau_oracle as O
+from attention_aspp_unet import AttentionASPPUNet
+import _capi
+cfg = O.NetCfg(base_c=16)
+net = AttentionASPPUNet(base_c=16)
+net.load_state_dict(O.make_state_dict(cfg, 1, 'R0'), strict=True)
+net.eval().prepare('cuda')
+net.set_option('graph', 0)
+net.set_option('fault_inject', 1)
+t0 = time.time()
+try:
+    net(torch.rand(1, 1, 64, 64, device='cuda'))
+    net.check_device()
+    print('NO_FAULT')
+except _capi.AauError as e:
+    print('FAULT_REPORTED %%.1fs %%s' %% (time.time() - t0, e))
+""" % (ROOT / "att-aspp-unet_b200", ROOT / "oracle")
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    out = r.stdout + r.stderr
+    assert "FAULT_REPORTED" in r.stdout, out[-2000:]
+    assert "code 102" in r.stdout and "MMA issuer waiting for operands" in r.stdout, r.stdout      # the code survived the trap
+    print("\n[fault path] %s (wall %.1f s)" % (r.stdout.strip()[:200], time.time() - t0))
+    # the GPU is fine for the next process / context
+    assert torch.zeros(4, device="cuda").sum().item() == 0.0
